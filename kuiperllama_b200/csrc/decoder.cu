@@ -1,0 +1,425 @@
+// Device-resident single-batch decoder: the per-token forward of LLama2Model / Qwen2Model
+// (kuiper/source/model/llama3.cpp:147-167, 600-745; qwen2.cpp) as a fixed chain of fused
+// launches captured ONCE in a CUDA graph and replayed for every position.
+//
+//   reference, per layer (15-18 launches)          here (6 launches)
+//   rmsnorm, wq, wk, wv [+3 bias adds]        ->   gemv_fused(norm -> q | k@cache | v@cache [+bias])
+//   rope (pos read on the host)               ->   rope (pos read from device memory)
+//   mha                                       ->   mha
+//   wo, add                                   ->   gemv_fused(wo, + residual)
+//   rmsnorm, w1, w3, swiglu                   ->   gemv_fused(norm -> w1|w3 -> silu*gate)
+//   w2, add                                   ->   gemv_fused(w2, + residual)
+//   final: rmsnorm, cls, argmax(+malloc+sync) ->   gemv_fused(norm -> cls), argmax+advance
+//
+// The position, the current token and the step counter live in device memory, so the
+// captured graph is position independent and a whole greedy run needs no host round trip
+// (reference: 2 blocking copies + 1 cudaMalloc per token, emb_kernel.cu:25-29,
+// argmax_kernel.cu:73-87).  Buffer roles follow llama3.cpp:425-500.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "../../include/kllm_b200.h"
+#include "kllm_device.cuh"
+#include "kllm_host.h"
+
+namespace kllm {
+
+struct StepState {  // device-resident loop state
+  int32_t token;    // input token of the current step
+  int32_t pos;      // position of the current step
+  int32_t step;     // steps done since generate() started
+  int32_t next;     // greedy id produced by the last step
+};
+
+__global__ void embed_token_kernel(const StepState* st, const float* __restrict__ table,
+                                   float* x, int dim, int vocab) {
+  const int32_t token = st->token;
+  if (token < 0 || token >= vocab) return;
+  const float4* s4 = reinterpret_cast<const float4*>(table + static_cast<size_t>(token) * dim);
+  float4* d4 = reinterpret_cast<float4*>(x);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (dim >> 2); i += gridDim.x * blockDim.x)
+    d4[i] = s4[i];
+}
+
+// Greedy argmax (argmax_kernel.cu:49-71 semantics: max value, lowest index) fused with the
+// loop bookkeeping: record the id, feed it (or the teacher's id) to the next step, pos += 1.
+__global__ void __launch_bounds__(1024)
+argmax_advance_kernel(const float* __restrict__ logits, int n, StepState* st, int32_t* out_tokens,
+                      const int32_t* teacher, int max_steps) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  float bv = 0.f;
+  int bi = -1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = logits[i];
+    if (bi < 0 || v > bv) {
+      bv = v;
+      bi = i;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto fold = [](float& v, int& i, float ov, int oi) {
+    if (oi >= 0 && (i < 0 || ov > v || (ov == v && oi < i))) {
+      v = ov;
+      i = oi;
+    }
+  };
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+    fold(bv, bi, __shfl_down_sync(kFull, bv, off), __shfl_down_sync(kFull, bi, off));
+  if (lane == 0) {
+    sv[warp] = bv;
+    si[warp] = bi;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    bv = sv[lane];
+    bi = si[lane];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+      fold(bv, bi, __shfl_down_sync(kFull, bv, off), __shfl_down_sync(kFull, bi, off));
+    if (lane == 0) {
+      const int next = bi < 0 ? 0 : bi;
+      const int step = st->step;
+      st->next = next;
+      if (out_tokens != nullptr && step < max_steps) out_tokens[step] = next;
+      st->token = (teacher != nullptr && step + 1 < max_steps) ? teacher[step + 1] : next;
+      st->pos = st->pos + 1;
+      st->step = step + 1;
+    }
+  }
+}
+
+}  // namespace kllm
+
+using namespace kllm;
+
+struct kllm_decoder {
+  kllm_decoder_desc d{};
+  std::vector<const float*> attn_norm, ffn_norm;
+  std::vector<const void*> wq, wk, wv, wo, w1, w2, w3;
+  std::vector<const float*> sq, sk, sv, so, s1, s2, s3, bq, bk, bv;
+  int kv_dim = 0, kv_mul = 0, head_size = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  // device buffers
+  float *x = nullptr, *q = nullptr, *attn = nullptr, *h = nullptr, *logits = nullptr;
+  float *score = nullptr, *kcache = nullptr, *vcache = nullptr, *sin_t = nullptr, *cos_t = nullptr;
+  float* tp_tmp = nullptr;
+  StepState* st = nullptr;
+  int32_t* out_tokens = nullptr;  // device [seq_len]
+  int32_t* teacher = nullptr;     // device [seq_len]
+  StepState* st_host = nullptr;   // pinned
+  int32_t* io_host = nullptr;     // pinned scratch
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;       // out_tokens recorded, no teacher
+  cudaGraph_t graph_tf = nullptr;
+  cudaGraphExec_t exec_tf = nullptr;    // teacher forced
+  int launches_per_step = 0;
+};
+
+namespace {
+
+#define KLLM_TRY(expr)                      \
+  do {                                      \
+    const int rc_ = static_cast<int>(expr); \
+    if (rc_ != 0) return rc_;               \
+  } while (0)
+
+template <typename T>
+std::vector<T> copy_ptrs(const T* src, int n) {
+  std::vector<T> v;
+  if (src != nullptr) v.assign(src, src + n);
+  return v;
+}
+
+int enqueue_step(kllm_decoder* dc, bool with_teacher, cudaStream_t s) {
+  const kllm_decoder_desc& d = dc->d;
+  const int dim = d.dim, L = d.layer_num, hid = d.hidden_dim;
+  const int q_rows = d.head_num * dc->head_size;  // == dim unless tensor-parallel
+  const int kvd = dc->kv_dim;
+  const float eps = flavour_eps(d.flavour);
+  const PosArg pos{&dc->st->pos, 0};
+  const bool tp = d.tp_size > 1;
+  const uint64_t before = launch_counter().load();
+
+  embed_token_kernel<<<4, 256, 0, s>>>(dc->st, d.tok_emb, dc->x, dim, d.vocab_size);
+  count_launch();
+  KLLM_TRY(cudaGetLastError());
+
+  for (int l = 0; l < L; ++l) {
+    const size_t layer_off = static_cast<size_t>(l) * d.seq_len * kvd;
+    // attention_rms + attention_qkv (llama3.cpp:600-640); k, v go straight into the cache row
+    {
+      kllm_gemv_job j{};
+      j.x = dc->x;
+      j.norm_w = dc->attn_norm[l];
+      j.norm_eps = eps;
+      j.in_dim = dim;
+      j.group_size = d.group_size;
+      j.n_seg = 3;
+      j.seg[0] = {dc->wq[l], d.group_size ? dc->sq[l] : nullptr, dc->bq.empty() ? nullptr : dc->bq[l],
+                  dc->q, q_rows};
+      j.seg[1] = {dc->wk[l], d.group_size ? dc->sk[l] : nullptr, dc->bk.empty() ? nullptr : dc->bk[l],
+                  dc->kcache + layer_off, kvd};
+      j.seg[2] = {dc->wv[l], d.group_size ? dc->sv[l] : nullptr, dc->bv.empty() ? nullptr : dc->bv[l],
+                  dc->vcache + layer_off, kvd};
+      GemvExtra ex;
+      ex.pos = pos;
+      ex.pos_stride[1] = kvd;
+      ex.pos_stride[2] = kvd;
+      KLLM_TRY(gemv_dispatch(&j, ex, s));
+    }
+    KLLM_TRY(launch_rope(d.flavour, q_rows, kvd, dc->head_size, dc->q, dc->kcache + layer_off, kvd,
+                         pos, dc->sin_t, dc->cos_t, s));
+    // attention_mha (llama3.cpp:652-676)
+    KLLM_TRY(launch_mha(pos, d.head_num, l, d.seq_len, kvd, dc->kv_mul, dc->head_size, dc->attn,
+                        dc->q, dc->score, dc->kcache, dc->vcache, s));
+    {
+      kllm_gemv_job j{};
+      j.x = dc->attn;
+      j.in_dim = q_rows;
+      j.group_size = d.group_size;
+      j.n_seg = 1;
+      j.seg[0] = {dc->wo[l], d.group_size ? dc->so[l] : nullptr, nullptr, tp ? dc->tp_tmp : dc->x, dim};
+      j.residual = tp ? nullptr : dc->x;  // feed_forward's first add (llama3.cpp:683-684)
+      KLLM_TRY(gemv_dispatch(&j, GemvExtra{}, s));
+      if (tp) {
+        KLLM_TRY(d.allreduce(d.allreduce_ctx, dc->tp_tmp, dim, s));
+        KLLM_TRY(kllm_add_f32(dc->x, dc->tp_tmp, dc->x, dim, s));
+      }
+    }
+    // feed_forward (llama3.cpp:686-720)
+    {
+      kllm_gemv_job j{};
+      j.x = dc->x;
+      j.norm_w = dc->ffn_norm[l];
+      j.norm_eps = eps;
+      j.in_dim = dim;
+      j.group_size = d.group_size;
+      j.n_seg = 2;
+      j.seg[0] = {dc->w1[l], d.group_size ? dc->s1[l] : nullptr, nullptr, dc->h, hid};
+      j.seg[1] = {dc->w3[l], d.group_size ? dc->s3[l] : nullptr, nullptr, nullptr, hid};
+      j.swiglu_pair = 1;
+      KLLM_TRY(gemv_dispatch(&j, GemvExtra{}, s));
+    }
+    {
+      kllm_gemv_job j{};
+      j.x = dc->h;
+      j.in_dim = hid;
+      j.group_size = d.group_size;
+      j.n_seg = 1;
+      j.seg[0] = {dc->w2[l], d.group_size ? dc->s2[l] : nullptr, nullptr, tp ? dc->tp_tmp : dc->x, dim};
+      j.residual = tp ? nullptr : dc->x;
+      KLLM_TRY(gemv_dispatch(&j, GemvExtra{}, s));
+      if (tp) {
+        KLLM_TRY(d.allreduce(d.allreduce_ctx, dc->tp_tmp, dim, s));
+        KLLM_TRY(kllm_add_f32(dc->x, dc->tp_tmp, dc->x, dim, s));
+      }
+    }
+  }
+  // cls_logits (llama3.cpp:722-731) + post_processing (:733-745)
+  {
+    kllm_gemv_job j{};
+    j.x = dc->x;
+    j.norm_w = d.final_norm;
+    j.norm_eps = eps;
+    j.in_dim = dim;
+    j.group_size = d.group_size;
+    j.n_seg = 1;
+    j.seg[0] = {d.wcls, d.group_size ? d.scls : nullptr, nullptr, dc->logits, d.vocab_size};
+    KLLM_TRY(gemv_dispatch(&j, GemvExtra{}, s));
+  }
+  argmax_advance_kernel<<<1, 1024, 0, s>>>(dc->logits, d.vocab_size, dc->st, dc->out_tokens,
+                                           with_teacher ? dc->teacher : nullptr, d.seq_len);
+  count_launch();
+  KLLM_TRY(cudaGetLastError());
+  dc->launches_per_step = static_cast<int>(launch_counter().load() - before);
+  return 0;
+}
+
+int capture(kllm_decoder* dc, bool with_teacher, cudaGraph_t* graph, cudaGraphExec_t* exec) {
+  KLLM_TRY(cudaStreamBeginCapture(dc->stream, cudaStreamCaptureModeRelaxed));
+  const int rc = enqueue_step(dc, with_teacher, dc->stream);
+  cudaGraph_t g = nullptr;
+  const cudaError_t end = cudaStreamEndCapture(dc->stream, &g);
+  if (rc != 0) {
+    if (g) cudaGraphDestroy(g);
+    return rc;
+  }
+  KLLM_TRY(end);
+  *graph = g;
+  KLLM_TRY(cudaGraphInstantiate(exec, g, 0));
+  // capturing does not execute: undo the launch accounting of the capture pass
+  launch_counter().fetch_sub(static_cast<uint64_t>(dc->launches_per_step));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kllm_decoder_create(const kllm_decoder_desc* desc, void* stream, kllm_decoder** out) {
+  if (!desc || !out) return KLLM_E_INVALID;
+  const kllm_decoder_desc& d = *desc;
+  if (d.dim <= 0 || d.hidden_dim <= 0 || d.layer_num <= 0 || d.head_num <= 0 ||
+      d.kv_head_num <= 0 || d.vocab_size <= 0 || d.seq_len <= 0)
+    return KLLM_E_INVALID;
+  if (!d.tok_emb || !d.attn_norm || !d.ffn_norm || !d.final_norm || !d.wq || !d.wk || !d.wv ||
+      !d.wo || !d.w1 || !d.w2 || !d.w3 || !d.wcls)
+    return KLLM_E_INVALID;
+  if (d.group_size > 0 && (!d.sq || !d.sk || !d.sv || !d.so || !d.s1 || !d.s2 || !d.s3 || !d.scls))
+    return KLLM_E_INVALID;
+  const int tp = d.tp_size > 1 ? d.tp_size : 1;
+  if (tp > 1 && d.allreduce == nullptr) return KLLM_E_INVALID;
+  // head_size from the FULL model: dim / (head_num * tp)
+  if (d.dim % (d.head_num * tp) != 0 || d.head_num % d.kv_head_num != 0) return KLLM_E_INVALID;
+  if ((d.dim & 3) != 0 || (d.hidden_dim & 3) != 0) return KLLM_E_UNSUPPORTED;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return KLLM_E_NODEVICE;
+
+  auto* dc = new kllm_decoder();
+  dc->d = d;
+  const int L = d.layer_num;
+  dc->attn_norm = copy_ptrs(d.attn_norm, L);
+  dc->ffn_norm = copy_ptrs(d.ffn_norm, L);
+  dc->wq = copy_ptrs(d.wq, L), dc->wk = copy_ptrs(d.wk, L), dc->wv = copy_ptrs(d.wv, L);
+  dc->wo = copy_ptrs(d.wo, L), dc->w1 = copy_ptrs(d.w1, L), dc->w2 = copy_ptrs(d.w2, L);
+  dc->w3 = copy_ptrs(d.w3, L);
+  if (d.group_size > 0) {
+    dc->sq = copy_ptrs(d.sq, L), dc->sk = copy_ptrs(d.sk, L), dc->sv = copy_ptrs(d.sv, L);
+    dc->so = copy_ptrs(d.so, L), dc->s1 = copy_ptrs(d.s1, L), dc->s2 = copy_ptrs(d.s2, L);
+    dc->s3 = copy_ptrs(d.s3, L);
+  }
+  dc->bq = copy_ptrs(d.bq, L), dc->bk = copy_ptrs(d.bk, L), dc->bv = copy_ptrs(d.bv, L);
+  dc->head_size = d.dim / (d.head_num * tp);
+  dc->kv_dim = d.kv_head_num * dc->head_size;
+  dc->kv_mul = d.head_num / d.kv_head_num;
+  dc->d.tp_size = tp;
+
+  if (stream != nullptr) {
+    dc->stream = static_cast<cudaStream_t>(stream);
+  } else {
+    if (cudaStreamCreateWithFlags(&dc->stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete dc;
+      return KLLM_E_NODEVICE;
+    }
+    dc->own_stream = true;
+  }
+
+  auto fail = [&](int rc) {
+    kllm_decoder_destroy(dc);
+    return rc;
+  };
+  auto dev_alloc = [&](float** p, size_t n) {
+    if (cudaMalloc(p, n * sizeof(float)) != cudaSuccess) return 1;
+    return static_cast<int>(cudaMemsetAsync(*p, 0, n * sizeof(float), dc->stream));
+  };
+  const size_t kv_elems = static_cast<size_t>(L) * d.seq_len * dc->kv_dim;
+  const int q_rows = d.head_num * dc->head_size;
+  if (dev_alloc(&dc->x, d.dim) || dev_alloc(&dc->q, q_rows) || dev_alloc(&dc->attn, q_rows) ||
+      dev_alloc(&dc->h, d.hidden_dim) || dev_alloc(&dc->logits, d.vocab_size) ||
+      dev_alloc(&dc->score, static_cast<size_t>(d.head_num) * d.seq_len) ||
+      dev_alloc(&dc->kcache, kv_elems) || dev_alloc(&dc->vcache, kv_elems) ||
+      dev_alloc(&dc->sin_t, static_cast<size_t>(d.seq_len) * dc->head_size) ||
+      dev_alloc(&dc->cos_t, static_cast<size_t>(d.seq_len) * dc->head_size) ||
+      dev_alloc(&dc->tp_tmp, d.dim))
+    return fail(static_cast<int>(cudaErrorMemoryAllocation));
+  if (cudaMalloc(&dc->st, sizeof(StepState)) != cudaSuccess ||
+      cudaMalloc(&dc->out_tokens, sizeof(int32_t) * d.seq_len) != cudaSuccess ||
+      cudaMalloc(&dc->teacher, sizeof(int32_t) * d.seq_len) != cudaSuccess ||
+      cudaMallocHost(&dc->st_host, sizeof(StepState)) != cudaSuccess ||
+      cudaMallocHost(&dc->io_host, sizeof(int32_t) * d.seq_len) != cudaSuccess)
+    return fail(static_cast<int>(cudaErrorMemoryAllocation));
+  cudaMemsetAsync(dc->st, 0, sizeof(StepState), dc->stream);
+
+  int rc = kllm_sincos_init(dc->head_size, d.seq_len, d.flavour, dc->sin_t, dc->cos_t, dc->stream);
+  if (rc != 0) return fail(rc);
+  if ((rc = capture(dc, false, &dc->graph, &dc->exec)) != 0) return fail(rc);
+  if ((rc = capture(dc, true, &dc->graph_tf, &dc->exec_tf)) != 0) return fail(rc);
+  if (cudaStreamSynchronize(dc->stream) != cudaSuccess) return fail(static_cast<int>(cudaGetLastError()));
+  *out = dc;
+  return 0;
+}
+
+void kllm_decoder_destroy(kllm_decoder* dc) {
+  if (!dc) return;
+  if (dc->stream) cudaStreamSynchronize(dc->stream);
+  if (dc->exec) cudaGraphExecDestroy(dc->exec);
+  if (dc->graph) cudaGraphDestroy(dc->graph);
+  if (dc->exec_tf) cudaGraphExecDestroy(dc->exec_tf);
+  if (dc->graph_tf) cudaGraphDestroy(dc->graph_tf);
+  float* bufs[] = {dc->x, dc->q, dc->attn, dc->h, dc->logits, dc->score,
+                   dc->kcache, dc->vcache, dc->sin_t, dc->cos_t, dc->tp_tmp};
+  for (float* b : bufs)
+    if (b) cudaFree(b);
+  if (dc->st) cudaFree(dc->st);
+  if (dc->out_tokens) cudaFree(dc->out_tokens);
+  if (dc->teacher) cudaFree(dc->teacher);
+  if (dc->st_host) cudaFreeHost(dc->st_host);
+  if (dc->io_host) cudaFreeHost(dc->io_host);
+  if (dc->own_stream && dc->stream) cudaStreamDestroy(dc->stream);
+  delete dc;
+}
+
+int kllm_decoder_step(kllm_decoder* dc, int32_t token_host, int32_t pos, int is_prompt,
+                      int32_t* next_host) {
+  if (!dc || !next_host) return KLLM_E_INVALID;
+  if (pos < 0 || pos >= dc->d.seq_len) return KLLM_E_INVALID;
+  StepState* hs = dc->st_host;
+  hs->token = token_host;
+  hs->pos = pos;
+  hs->step = 0;
+  hs->next = -1;
+  KLLM_TRY(cudaMemcpyAsync(dc->st, hs, sizeof(StepState), cudaMemcpyHostToDevice, dc->stream));
+  KLLM_TRY(cudaGraphLaunch(dc->exec, dc->stream));
+  count_launch(static_cast<uint64_t>(dc->launches_per_step));
+  KLLM_TRY(cudaMemcpyAsync(hs, dc->st, sizeof(StepState), cudaMemcpyDeviceToHost, dc->stream));
+  KLLM_TRY(cudaStreamSynchronize(dc->stream));
+  *next_host = is_prompt ? -1 : hs->next;
+  return 0;
+}
+
+int kllm_decoder_generate(kllm_decoder* dc, int32_t first_token, int32_t start_pos,
+                          int32_t n_steps, const int32_t* teacher_host,
+                          int32_t* out_tokens_host) {
+  if (!dc || n_steps <= 0 || start_pos < 0) return KLLM_E_INVALID;
+  if (start_pos + n_steps > dc->d.seq_len) return KLLM_E_INVALID;
+  StepState* hs = dc->st_host;
+  hs->token = teacher_host ? teacher_host[0] : first_token;
+  hs->pos = start_pos;
+  hs->step = 0;
+  hs->next = -1;
+  KLLM_TRY(cudaMemcpyAsync(dc->st, hs, sizeof(StepState), cudaMemcpyHostToDevice, dc->stream));
+  if (teacher_host) {
+    std::memcpy(dc->io_host, teacher_host, sizeof(int32_t) * n_steps);
+    KLLM_TRY(cudaMemcpyAsync(dc->teacher, dc->io_host, sizeof(int32_t) * n_steps,
+                             cudaMemcpyHostToDevice, dc->stream));
+  }
+  cudaGraphExec_t exec = teacher_host ? dc->exec_tf : dc->exec;
+  for (int i = 0; i < n_steps; ++i) KLLM_TRY(cudaGraphLaunch(exec, dc->stream));
+  count_launch(static_cast<uint64_t>(dc->launches_per_step) * n_steps);
+  if (out_tokens_host) {
+    KLLM_TRY(cudaMemcpyAsync(dc->io_host, dc->out_tokens, sizeof(int32_t) * n_steps,
+                             cudaMemcpyDeviceToHost, dc->stream));
+  }
+  KLLM_TRY(cudaStreamSynchronize(dc->stream));
+  if (out_tokens_host) std::memcpy(out_tokens_host, dc->io_host, sizeof(int32_t) * n_steps);
+  return 0;
+}
+
+int kllm_decoder_logits(kllm_decoder* dc, float* logits_host) {
+  if (!dc || !logits_host) return KLLM_E_INVALID;
+  KLLM_TRY(cudaStreamSynchronize(dc->stream));
+  return static_cast<int>(cudaMemcpy(logits_host, dc->logits, sizeof(float) * dc->d.vocab_size,
+                                     cudaMemcpyDeviceToHost));
+}
+
+const float* kllm_decoder_key_cache(kllm_decoder* dc) { return dc ? dc->kcache : nullptr; }
+const float* kllm_decoder_value_cache(kllm_decoder* dc) { return dc ? dc->vcache : nullptr; }
+int kllm_decoder_launches_per_step(const kllm_decoder* dc) { return dc ? dc->launches_per_step : 0; }
+
+}  // extern "C"
