@@ -166,5 +166,5 @@ def to_device(w: dict, device="cuda"):
     for k, v in w.items():
         if k.startswith("_"):
             continue
-        out[k] = None if v is None else torch.from_numpy(np.ascontiguousarray(v)).to(device)
+        out[k] = None if v is None else torch.from_numpy(np.array(v, copy=True)).to(device)
     return out

@@ -151,7 +151,7 @@ def test_teacher_forced_generate_and_determinism(kllm_lib):
     inputs = [1] + free[:-1]
     forced = dec.generate(0, 0, 100, teacher=inputs)
     assert forced == free
-    assert 100 <= dec.launches_per_step * 1 and dec.launches_per_step == 6 * shape.layer_num + 3
+    assert dec.launches_per_step == 6 * shape.layer_num + 3
     dec.close()
 
 
