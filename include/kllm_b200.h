@@ -184,8 +184,12 @@ int kllm_decoder_generate(kllm_decoder* dec, int32_t first_token, int32_t start_
 int kllm_decoder_logits(kllm_decoder* dec, float* logits_host);
 const float* kllm_decoder_key_cache(kllm_decoder* dec);   /* device [L, seq_len, kv_dim] */
 const float* kllm_decoder_value_cache(kllm_decoder* dec); /* device */
-/* Kernel launches one decode step issues (graph nodes). */
+/* Kernel launches one decode step issues (graph nodes; 1 for the persistent engine). */
 int kllm_decoder_launches_per_step(const kllm_decoder* dec);
+/* "persistent": one cooperative megakernel launch runs whole positions with a TMA-fed weight
+ * ring; "graph": CUDA-graph chain of fused launches (shapes the ring does not handle, tensor
+ * parallel).  Environment KLLM_ENGINE=graph|persistent forces a choice at create time. */
+const char* kllm_decoder_engine(const kllm_decoder* dec);
 
 #ifdef __cplusplus
 }

@@ -90,6 +90,7 @@ _SIGNATURES = {
     "kllm_decoder_key_cache": (c_void_p, [c_void_p]),
     "kllm_decoder_value_cache": (c_void_p, [c_void_p]),
     "kllm_decoder_launches_per_step": (c_int, [c_void_p]),
+    "kllm_decoder_engine": (c_char_p, [c_void_p]),
 }
 
 _lib = None

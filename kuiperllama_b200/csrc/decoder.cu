@@ -18,12 +18,14 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "../../include/kllm_b200.h"
 #include "kllm_device.cuh"
 #include "kllm_host.h"
+#include "megakernel.h"
 
 namespace kllm {
 
@@ -109,6 +111,9 @@ struct kllm_decoder {
   float *x = nullptr, *q = nullptr, *attn = nullptr, *h = nullptr, *logits = nullptr;
   float *score = nullptr, *kcache = nullptr, *vcache = nullptr, *sin_t = nullptr, *cos_t = nullptr;
   float* tp_tmp = nullptr;
+  float* k_raw = nullptr;  // persistent engine: un-rotated key row of the current position
+  MegaEngine mega;
+  bool use_mega = false;
   StepState* st = nullptr;
   int32_t* out_tokens = nullptr;  // device [seq_len]
   int32_t* teacher = nullptr;     // device [seq_len]
@@ -326,7 +331,7 @@ int kllm_decoder_create(const kllm_decoder_desc* desc, void* stream, kllm_decode
       dev_alloc(&dc->kcache, kv_elems) || dev_alloc(&dc->vcache, kv_elems) ||
       dev_alloc(&dc->sin_t, static_cast<size_t>(d.seq_len) * dc->head_size) ||
       dev_alloc(&dc->cos_t, static_cast<size_t>(d.seq_len) * dc->head_size) ||
-      dev_alloc(&dc->tp_tmp, d.dim))
+      dev_alloc(&dc->tp_tmp, d.dim) || dev_alloc(&dc->k_raw, dc->kv_dim))
     return fail(static_cast<int>(cudaErrorMemoryAllocation));
   if (cudaMalloc(&dc->st, sizeof(StepState)) != cudaSuccess ||
       cudaMalloc(&dc->out_tokens, sizeof(int32_t) * d.seq_len) != cudaSuccess ||
@@ -338,8 +343,47 @@ int kllm_decoder_create(const kllm_decoder_desc* desc, void* stream, kllm_decode
 
   int rc = kllm_sincos_init(dc->head_size, d.seq_len, d.flavour, dc->sin_t, dc->cos_t, dc->stream);
   if (rc != 0) return fail(rc);
-  if ((rc = capture(dc, false, &dc->graph, &dc->exec)) != 0) return fail(rc);
-  if ((rc = capture(dc, true, &dc->graph_tf, &dc->exec_tf)) != 0) return fail(rc);
+  // Engine: the persistent megakernel (one cooperative launch per run) when the shape fits its
+  // shared-memory ring, else the CUDA-graph chain of fused launches.  KLLM_ENGINE=graph|persistent
+  // forces one (persistent fails loudly if unsupported).  Both are CUDA; neither is a fallback to
+  // anything off-device.
+  const char* want = getenv("KLLM_ENGINE");
+  const bool force_graph = want != nullptr && strcmp(want, "graph") == 0;
+  const bool force_mega = want != nullptr && strcmp(want, "persistent") == 0;
+  if (!force_graph && tp == 1) {
+    MegaModel mm{};
+    mm.dim = d.dim, mm.hidden_dim = d.hidden_dim, mm.layer_num = L, mm.head_num = d.head_num;
+    mm.kv_head_num = d.kv_head_num, mm.vocab_size = d.vocab_size, mm.seq_len = d.seq_len;
+    mm.head_size = dc->head_size, mm.kv_dim = dc->kv_dim, mm.kv_mul = dc->kv_mul;
+    mm.flavour = d.flavour, mm.group_size = d.group_size;
+    mm.tok_emb = d.tok_emb, mm.attn_norm = dc->attn_norm.data(), mm.ffn_norm = dc->ffn_norm.data();
+    mm.final_norm = d.final_norm;
+    mm.wq = dc->wq.data(), mm.wk = dc->wk.data(), mm.wv = dc->wv.data(), mm.wo = dc->wo.data();
+    mm.w1 = dc->w1.data(), mm.w2 = dc->w2.data(), mm.w3 = dc->w3.data(), mm.wcls = d.wcls;
+    if (d.group_size > 0) {
+      mm.sq = dc->sq.data(), mm.sk = dc->sk.data(), mm.sv = dc->sv.data(), mm.so = dc->so.data();
+      mm.s1 = dc->s1.data(), mm.s2 = dc->s2.data(), mm.s3 = dc->s3.data(), mm.scls = d.scls;
+    }
+    mm.bq = dc->bq.empty() ? nullptr : dc->bq.data();
+    mm.bk = dc->bk.empty() ? nullptr : dc->bk.data();
+    mm.bv = dc->bv.empty() ? nullptr : dc->bv.data();
+    mm.x = dc->x, mm.q = dc->q, mm.k_raw = dc->k_raw, mm.attn_out = dc->attn, mm.h = dc->h;
+    mm.logits = dc->logits, mm.score = dc->score, mm.key_cache = dc->kcache, mm.value_cache = dc->vcache;
+    mm.sin_cache = dc->sin_t, mm.cos_cache = dc->cos_t, mm.state = dc->st, mm.out_tokens = dc->out_tokens;
+    rc = dc->mega.init(mm, dc->stream);
+    if (rc == 0) {
+      dc->use_mega = true;
+      dc->launches_per_step = 1;
+    } else if (rc != KLLM_E_UNSUPPORTED || force_mega) {
+      return fail(rc);
+    }
+  } else if (force_mega) {
+    return fail(KLLM_E_UNSUPPORTED);
+  }
+  if (!dc->use_mega) {
+    if ((rc = capture(dc, false, &dc->graph, &dc->exec)) != 0) return fail(rc);
+    if ((rc = capture(dc, true, &dc->graph_tf, &dc->exec_tf)) != 0) return fail(rc);
+  }
   if (cudaStreamSynchronize(dc->stream) != cudaSuccess) return fail(static_cast<int>(cudaGetLastError()));
   *out = dc;
   return 0;
@@ -348,12 +392,13 @@ int kllm_decoder_create(const kllm_decoder_desc* desc, void* stream, kllm_decode
 void kllm_decoder_destroy(kllm_decoder* dc) {
   if (!dc) return;
   if (dc->stream) cudaStreamSynchronize(dc->stream);
+  dc->mega.destroy();
   if (dc->exec) cudaGraphExecDestroy(dc->exec);
   if (dc->graph) cudaGraphDestroy(dc->graph);
   if (dc->exec_tf) cudaGraphExecDestroy(dc->exec_tf);
   if (dc->graph_tf) cudaGraphDestroy(dc->graph_tf);
   float* bufs[] = {dc->x, dc->q, dc->attn, dc->h, dc->logits, dc->score,
-                   dc->kcache, dc->vcache, dc->sin_t, dc->cos_t, dc->tp_tmp};
+                   dc->kcache, dc->vcache, dc->sin_t, dc->cos_t, dc->tp_tmp, dc->k_raw};
   for (float* b : bufs)
     if (b) cudaFree(b);
   if (dc->st) cudaFree(dc->st);
@@ -375,8 +420,12 @@ int kllm_decoder_step(kllm_decoder* dc, int32_t token_host, int32_t pos, int is_
   hs->step = 0;
   hs->next = -1;
   KLLM_TRY(cudaMemcpyAsync(dc->st, hs, sizeof(StepState), cudaMemcpyHostToDevice, dc->stream));
-  KLLM_TRY(cudaGraphLaunch(dc->exec, dc->stream));
-  count_launch(static_cast<uint64_t>(dc->launches_per_step));
+  if (dc->use_mega) {
+    KLLM_TRY(dc->mega.run(1, nullptr));
+  } else {
+    KLLM_TRY(cudaGraphLaunch(dc->exec, dc->stream));
+    count_launch(static_cast<uint64_t>(dc->launches_per_step));
+  }
   KLLM_TRY(cudaMemcpyAsync(hs, dc->st, sizeof(StepState), cudaMemcpyDeviceToHost, dc->stream));
   KLLM_TRY(cudaStreamSynchronize(dc->stream));
   *next_host = is_prompt ? -1 : hs->next;
@@ -399,9 +448,13 @@ int kllm_decoder_generate(kllm_decoder* dc, int32_t first_token, int32_t start_p
     KLLM_TRY(cudaMemcpyAsync(dc->teacher, dc->io_host, sizeof(int32_t) * n_steps,
                              cudaMemcpyHostToDevice, dc->stream));
   }
-  cudaGraphExec_t exec = teacher_host ? dc->exec_tf : dc->exec;
-  for (int i = 0; i < n_steps; ++i) KLLM_TRY(cudaGraphLaunch(exec, dc->stream));
-  count_launch(static_cast<uint64_t>(dc->launches_per_step) * n_steps);
+  if (dc->use_mega) {
+    KLLM_TRY(dc->mega.run(n_steps, teacher_host ? dc->teacher : nullptr));
+  } else {
+    cudaGraphExec_t exec = teacher_host ? dc->exec_tf : dc->exec;
+    for (int i = 0; i < n_steps; ++i) KLLM_TRY(cudaGraphLaunch(exec, dc->stream));
+    count_launch(static_cast<uint64_t>(dc->launches_per_step) * n_steps);
+  }
   if (out_tokens_host) {
     KLLM_TRY(cudaMemcpyAsync(dc->io_host, dc->out_tokens, sizeof(int32_t) * n_steps,
                              cudaMemcpyDeviceToHost, dc->stream));
@@ -421,5 +474,9 @@ int kllm_decoder_logits(kllm_decoder* dc, float* logits_host) {
 const float* kllm_decoder_key_cache(kllm_decoder* dc) { return dc ? dc->kcache : nullptr; }
 const float* kllm_decoder_value_cache(kllm_decoder* dc) { return dc ? dc->vcache : nullptr; }
 int kllm_decoder_launches_per_step(const kllm_decoder* dc) { return dc ? dc->launches_per_step : 0; }
+const char* kllm_decoder_engine(const kllm_decoder* dc) {
+  if (!dc) return "";
+  return dc->use_mega ? "persistent" : "graph";
+}
 
 }  // extern "C"

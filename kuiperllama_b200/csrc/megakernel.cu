@@ -1,0 +1,893 @@
+// Persistent decode megakernel for sm_100a: the whole per-token forward of LLama2Model /
+// Qwen2Model (kuiper/source/model/llama3.cpp:147-167, 600-745) in ONE cooperative launch that
+// can run any number of consecutive positions.
+//
+// Why: at batch 1 the path is a 4-26 GB/token weight stream; with one launch per op (even 6
+// fused launches per layer in a CUDA graph) every kernel boundary drains the HBM pipeline
+// (profiles/r01a: 15-42 % DRAM utilisation per kernel).  Here one CTA per SM stays resident
+// and a dedicated producer warp streams that CTA's share of EVERY weight matrix, in schedule
+// order, through a ring of shared-memory stages with TMA bulk copies (cp.async.bulk ->
+// UBLKCP) signalled on mbarriers.  Weights never depend on activations, so the producer runs
+// ahead across phase boundaries, grid barriers and the attention phase: HBM keeps streaming
+// while consumers wait for each other, and the ~190 KB/SM of ring (28 MB chip-wide, ~4 us of
+// HBM time) absorbs every such stall.
+//
+// Schedule per layer (5 grid barriers):  QKV(+bias) | attention(+RoPE) | Wo+residual |
+// W1,W3->SiLU*gate | W2+residual ; then classifier + greedy argmax.  RoPE moves into the
+// attention phase so GEMV rows can be split evenly over all SMs.
+//
+// Arithmetic is the same as the per-op kernels (gemv.cu / attention.cu / elementwise.cu): every
+// dot product, reduction tree, softmax sum and value chain reproduces the reference CUDA
+// kernels' floating-point order, so logits stay bit-identical to the reference's CUDA path.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <cstdint>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../include/kllm_b200.h"
+#include "kllm_device.cuh"
+#include "kllm_host.h"
+#include "megakernel.h"
+
+namespace kllm {
+namespace mega {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kThreads = kConsumerThreads + 32;  // + one producer warp
+constexpr int kMaxStages = 16;
+constexpr int kVTile = 32;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                         uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+}
+
+struct Pipe {
+  int slot;
+  uint32_t parity;
+  __device__ __forceinline__ void advance(int stages) {
+    if (++slot == stages) {
+      slot = 0;
+      parity ^= 1u;
+    }
+  }
+};
+
+// Grid barrier over the consumer threads of all CTAs.  Monotonic counter, wrap-safe compare.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target, unsigned grid) {
+  consumer_sync();
+  target += grid;
+  if (threadIdx.x == 0) {
+    red_release_add(counter, 1u);
+    while (static_cast<int>(ld_acquire_u32(counter) - target) < 0) {
+    }
+  }
+  consumer_sync();
+}
+
+// ---- unit -> (segment, row) ------------------------------------------------------------------
+struct RowRef {
+  int seg;
+  int row;
+};
+__device__ __forceinline__ RowRef resolve_row(const Phase& ph, int unit, int sub) {
+  if (ph.swiglu) return RowRef{sub, unit};
+  int seg = 0, row = unit;
+  if (ph.n_seg > 1 && row >= ph.seg[0].rows) {
+    row -= ph.seg[0].rows;
+    seg = 1;
+    if (ph.n_seg > 2 && row >= ph.seg[1].rows) {
+      row -= ph.seg[1].rows;
+      seg = 2;
+    }
+  }
+  return RowRef{seg, row};
+}
+
+// ---- exact-order accumulation from shared memory ----------------------------------------------
+// fp32: virtual thread (lane + 32 j) owns packs base + 32 j + lane (matmul_kernel.cu:27-35).
+template <int NR>
+__device__ __forceinline__ void accum_f32(const float4* const (&w)[NR], const float4* x4,
+                                          int n_packs, int lane, float (&acc)[NR][4]) {
+  for (int base = 0; base < n_packs; base += 128) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = base + 32 * j + lane;
+      if (idx < n_packs) {
+        const float4 xv = x4[idx];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[r][j] = __fadd_rn(dot4_ref(xv, w[r][idx]), acc[r][j]);
+      }
+    }
+  }
+}
+
+// int8: virtual thread (4 lane + e) owns elements 128 k + 4 lane + e (matmul_kernel.cu:70-74).
+template <int NR>
+__device__ __forceinline__ void accum_w8(const uint32_t* const (&w)[NR], const float* const (&sc)[NR],
+                                         const long long (&ebase)[NR], const float4* x4, int M,
+                                         int group_shift, int group_size, int lane,
+                                         float (&acc)[NR][4]) {
+  const int chunks = (M + 127) >> 7;
+  for (int k = 0; k < chunks; ++k) {
+    const int i = (k << 7) + (lane << 2);
+    if (i < M) {
+      const float4 xv = x4[i >> 2];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const uint32_t packed = w[r][i >> 2];
+        // scales of this row staged from the first group the row touches
+        const long long e = ebase[r] + i;
+        const long long g0 = group_shift >= 0 ? (ebase[r] >> group_shift) : (ebase[r] / group_size);
+        const long long g = group_shift >= 0 ? (e >> group_shift) : (e / group_size);
+        const float s = sc[r][g - g0];
+        float wf[4];
+        int8x4_to_float(packed, wf);
+        acc[r][0] = __fmaf_rn(__fmul_rn(xv.x, s), wf[0], acc[r][0]);
+        acc[r][1] = __fmaf_rn(__fmul_rn(xv.y, s), wf[1], acc[r][1]);
+        acc[r][2] = __fmaf_rn(__fmul_rn(xv.z, s), wf[2], acc[r][2]);
+        acc[r][3] = __fmaf_rn(__fmul_rn(xv.w, s), wf[3], acc[r][3]);
+      }
+    }
+  }
+}
+
+// rmsnorm_kernel.cu:4-50 on x staged in shared memory (warp 0), cf. gemv.cu rms_scale_ref.
+__device__ __forceinline__ float rms_scale_smem(const float* xs, int n, float eps, int lane) {
+  const int pack_num = n >> 2;
+  const float4* xs4 = reinterpret_cast<const float4*>(xs);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int base = 0; base < pack_num; base += 128) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = base + 32 * j + lane;
+      if (idx < pack_num) {
+        const float4 v = xs4[idx];
+        float s = acc[j];
+        s = __fmaf_rn(v.x, v.x, s);
+        s = __fmaf_rn(v.y, v.y, s);
+        s = __fmaf_rn(v.z, v.z, s);
+        s = __fmaf_rn(v.w, v.w, s);
+        acc[j] = s;
+      }
+    }
+  }
+  float sum = block128_sum_vt(acc);
+  sum = __shfl_sync(kFull, sum, 0);
+  return rsqrtf(__fadd_rn(__fdiv_rn(sum, static_cast<float>(n)), eps));
+}
+
+struct ArgBest {
+  float v;
+  int i;
+};
+__device__ __forceinline__ void arg_fold(ArgBest& a, float ov, int oi) {
+  if (oi >= 0 && (a.i < 0 || ov > a.v || (ov == a.v && oi < a.i))) {
+    a.v = ov;
+    a.i = oi;
+  }
+}
+
+// ---- attention phase: one CTA per query head (mha_kernel.cu:47-110 + rope_kernel.cu) ------------
+__device__ void attention_phase(const Params& P, const Phase& ph, int head, int pos, float* ws,
+                                float* s_warp, float* s_bcast) {
+  const int tid = threadIdx.x;
+  const int hs = P.head_size, kv_dim = P.kv_dim, seq_len = P.seq_len;
+  float* q_s = ws;             // [hs]
+  float* k_s = ws + hs;        // [hs] rotated key of the current position
+  float* v_s = ws + 2 * hs;    // [2][kVTile][hs]
+  const int kvh = head / P.kv_mul;
+  const int head_offset = kvh * hs;
+  const long long layer_offset = static_cast<long long>(ph.layer) * seq_len * kv_dim;
+  float* kcache = P.key_cache + layer_offset + head_offset;
+  const float* vcache = P.value_cache + layer_offset + head_offset;
+  float* score_head = P.score + static_cast<size_t>(head) * seq_len;
+
+  // RoPE on q (this head) and on the new key row (this head's kv head), rope_kernel.cu as
+  // compiled (see elementwise.cu): interleaved pairs or half-split pairs.
+  if (tid < hs / 2) {
+    const float* qg = P.q + static_cast<size_t>(head) * hs;
+    const float* kg = P.k_raw + head_offset;
+    int i0, i1, ci;
+    if (P.flavour == KLLM_FLAVOUR_LLAMA2) {
+      i0 = 2 * tid, i1 = 2 * tid + 1, ci = 2 * tid;  // head_dim = idx % head_size
+    } else {
+      i0 = tid, i1 = tid + hs / 2, ci = 2 * tid;      // sin[pos*hs + head_dim*2]
+    }
+    const float fci = P.sin_cache[static_cast<size_t>(pos) * hs + ci];
+    const float fcr = P.cos_cache[static_cast<size_t>(pos) * hs + ci];
+    const float q0 = __ldcg(qg + i0), q1 = __ldcg(qg + i1);
+    q_s[i0] = __fmaf_rn(fcr, q0, -__fmul_rn(fci, q1));
+    q_s[i1] = __fmaf_rn(fci, q0, __fmul_rn(fcr, q1));
+    const float k0 = __ldcg(kg + i0), k1 = __ldcg(kg + i1);
+    const float r0 = __fmaf_rn(fcr, k0, -__fmul_rn(fci, k1));
+    const float r1 = __fmaf_rn(fci, k0, __fmul_rn(fcr, k1));
+    k_s[i0] = r0;
+    k_s[i1] = r1;
+    if (head % P.kv_mul == 0) {  // one writer per kv head puts the rotated key into the cache
+      kcache[static_cast<size_t>(pos) * kv_dim + i0] = r0;
+      kcache[static_cast<size_t>(pos) * kv_dim + i1] = r1;
+    }
+  }
+  consumer_sync();
+
+  const float scale = 1.f / sqrtf(static_cast<float>(hs));
+  const float4* q4 = reinterpret_cast<const float4*>(q_s);
+  for (int t = tid; t <= pos; t += kConsumerThreads) {
+    const float4* k4 = (t == pos) ? reinterpret_cast<const float4*>(k_s)
+                                  : reinterpret_cast<const float4*>(kcache + static_cast<size_t>(t) * kv_dim);
+    float score = 0.0f;
+#pragma unroll 4
+    for (int i = 0; i < (hs >> 2); ++i) {
+      const float4 kv = k4[i];
+      const float4 qv = q4[i];
+      score = __fmaf_rn(kv.x, qv.x, score);
+      score = __fmaf_rn(kv.y, qv.y, score);
+      score = __fmaf_rn(kv.z, qv.z, score);
+      score = __fmaf_rn(kv.w, qv.w, score);
+    }
+    score_head[t] = __fmul_rn(score, scale);
+  }
+  consumer_sync();
+
+  // softmax, mha_kernel.cu:7-45 (256 strided lanes + cub block reduce order)
+  const int size = pos + 1;
+  const int lane = tid & 31, warp = tid >> 5;
+  float max_val = tid < size ? score_head[tid] : -FLT_MAX;
+  for (int i = tid + kConsumerThreads; i < size; i += kConsumerThreads)
+    max_val = fmaxf(max_val, score_head[i]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) max_val = fmaxf(max_val, __shfl_xor_sync(kFull, max_val, off));
+  if (lane == 0) s_warp[warp] = max_val;
+  consumer_sync();
+  max_val = s_warp[0];
+#pragma unroll
+  for (int w = 1; w < kConsumerWarps; ++w) max_val = fmaxf(max_val, s_warp[w]);
+  consumer_sync();
+
+  float sum = 0.0f;
+  for (int i = tid; i < size; i += kConsumerThreads) {
+    const float e = expf(score_head[i] - max_val);
+    score_head[i] = e;
+    sum += e;
+  }
+  sum = warp_tree_sum(sum);
+  if (lane == 0) s_warp[warp] = sum;
+  consumer_sync();
+  if (tid == 0) {
+    float total = s_warp[0];
+#pragma unroll
+    for (int w = 1; w < kConsumerWarps; ++w) total = __fadd_rn(total, s_warp[w]);
+    *s_bcast = total;
+  }
+  consumer_sync();
+  sum = *s_bcast;
+  for (int i = tid; i < size; i += kConsumerThreads) score_head[i] = score_head[i] / sum;
+  consumer_sync();
+
+  // weighted value sum, mha_kernel.cu:97-109: one FFMA chain per output element
+  const int vec_per_row = hs >> 2;
+  const int n_tiles = (size + kVTile - 1) / kVTile;
+  auto stage = [&](int tile, int buf) {
+    const int t0 = tile * kVTile;
+    float4* dst = reinterpret_cast<float4*>(v_s + static_cast<size_t>(buf) * kVTile * hs);
+    for (int e = tid; e < kVTile * vec_per_row; e += kConsumerThreads) {
+      const int tt = e / vec_per_row, c = e % vec_per_row;
+      if (t0 + tt <= pos)
+        dst[e] = *reinterpret_cast<const float4*>(vcache + static_cast<size_t>(t0 + tt) * kv_dim + 4 * c);
+    }
+  };
+  float value = 0.0f;
+  stage(0, 0);
+  consumer_sync();
+  for (int tile = 0; tile < n_tiles; ++tile) {
+    const int buf = tile & 1;
+    if (tile + 1 < n_tiles) stage(tile + 1, buf ^ 1);
+    if (tid < hs) {
+      const float* vt = v_s + static_cast<size_t>(buf) * kVTile * hs + tid;
+      const int t0 = tile * kVTile;
+      const int cnt = min(kVTile, size - t0);
+#pragma unroll 8
+      for (int tt = 0; tt < cnt; ++tt) value = __fmaf_rn(score_head[t0 + tt], vt[tt * hs], value);
+    }
+    consumer_sync();
+  }
+  if (tid < hs) P.attn_out[static_cast<size_t>(head) * hs + tid] = value;
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t full_bar[kMaxStages];
+  __shared__ uint64_t empty_bar[kMaxStages];
+  __shared__ float s_warp[kConsumerWarps];
+  __shared__ float s_bcast;
+  __shared__ float s_argv[kConsumerWarps];
+  __shared__ int s_argi[kConsumerWarps];
+
+  float* xs = reinterpret_cast<float*>(smem);
+  unsigned char* stages = smem + P.xbuf_bytes;
+  const int S = P.num_stages;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const bool is_producer = warp == kConsumerWarps;
+  const int cta = blockIdx.x;
+  const int G = gridDim.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  Pipe pipe{0, 0u};
+  const int wbytes = P.group_size > 0 ? 1 : 4;
+
+  // =============================== producer warp ===============================================
+  if (is_producer) {
+    const uint64_t policy = policy_evict_first();
+    for (int tok = 0; tok < P.n_tokens; ++tok) {
+      for (int pi = 0; pi < P.n_phases; ++pi) {
+        const Phase& ph = P.phases[pi];
+        if (ph.kind != kPhaseGemv) continue;
+        const int u0 = static_cast<int>(static_cast<long long>(cta) * ph.units / G);
+        const int u1 = static_cast<int>(static_cast<long long>(cta + 1) * ph.units / G);
+        const int rpu = ph.swiglu ? 2 : 1;
+        const int row_bytes = ph.in_dim * wbytes;
+        if (ph.chunks_per_row == 1) {
+          const int ups = ph.rows_per_stage / rpu;
+          for (int u = u0; u < u1; u += ups) {
+            const int n = min(ups, u1 - u);
+            const int nrows = n * rpu;
+            mbar_wait(&empty_bar[pipe.slot], pipe.parity ^ 1u);
+            unsigned char* dst = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
+            if (lane == 0)
+              mbar_expect_tx(&full_bar[pipe.slot],
+                             static_cast<uint32_t>(nrows) * (row_bytes + ph.scale_row_bytes));
+            __syncwarp();
+            for (int i = lane; i < nrows; i += 32) {
+              const RowRef rr = resolve_row(ph, u + i / rpu, i % rpu);
+              const long long e = static_cast<long long>(rr.row) * ph.in_dim;
+              const unsigned char* src = static_cast<const unsigned char*>(ph.seg[rr.seg].w) + e * wbytes;
+              bulk_g2s(dst + static_cast<size_t>(i) * row_bytes, src, row_bytes,
+                       &full_bar[pipe.slot], policy);
+              if (ph.scale_row_bytes) {
+                const long long g0 = ph.group_shift >= 0 ? (e >> ph.group_shift) : (e / ph.group_size);
+                bulk_g2s(dst + ph.scale_off + static_cast<size_t>(i) * ph.scale_row_bytes,
+                         ph.seg[rr.seg].scales + g0, ph.scale_row_bytes, &full_bar[pipe.slot],
+                         policy);
+              }
+            }
+            pipe.advance(S);
+          }
+        } else {
+          for (int u = u0; u < u1; ++u) {
+            const RowRef rr = resolve_row(ph, u, 0);
+            const unsigned char* src = static_cast<const unsigned char*>(ph.seg[rr.seg].w) +
+                                       static_cast<long long>(rr.row) * row_bytes;
+            for (int c = 0; c < ph.chunks_per_row; ++c) {
+              const int e0 = c * ph.chunk_elems;
+              const int ne = min(ph.chunk_elems, ph.in_dim - e0);
+              mbar_wait(&empty_bar[pipe.slot], pipe.parity ^ 1u);
+              if (lane == 0) {
+                mbar_expect_tx(&full_bar[pipe.slot], static_cast<uint32_t>(ne) * wbytes);
+                bulk_g2s(stages + static_cast<size_t>(pipe.slot) * P.stage_bytes,
+                         src + static_cast<size_t>(e0) * wbytes, static_cast<uint32_t>(ne) * wbytes,
+                         &full_bar[pipe.slot], policy);
+              }
+              __syncwarp();
+              pipe.advance(S);
+            }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // =============================== consumer warps ===============================================
+  unsigned bar_target = P.barrier_base;
+  int token = P.state->token;
+  if (static_cast<unsigned>(token) >= static_cast<unsigned>(P.vocab_size)) token = 0;
+  int pos = P.state->pos;
+  int step = P.state->step;
+
+  for (int tok = 0; tok < P.n_tokens; ++tok) {
+    const float* emb_row = P.tok_emb + static_cast<size_t>(token) * P.dim;
+    ArgBest best{0.f, -1};
+
+    for (int pi = 0; pi < P.n_phases; ++pi) {
+      const Phase& ph = P.phases[pi];
+
+      if (ph.kind == kPhaseAttention) {
+        if (cta < P.head_num) attention_phase(P, ph, cta, pos, xs, s_warp, &s_bcast);
+        grid_barrier(P.barrier, bar_target, G);
+        continue;
+      }
+
+      // ---- stage the input vector (and RMS-normalise it) --------------------------------------
+      const int M = ph.in_dim;
+      {
+        const float* xg = ph.x_from_emb ? emb_row : ph.x;
+        const float4* xg4 = reinterpret_cast<const float4*>(xg);
+        float4* xs4w = reinterpret_cast<float4*>(xs);
+        for (int i = tid; i < (M >> 2); i += kConsumerThreads) xs4w[i] = __ldcg(xg4 + i);
+        consumer_sync();
+        if (ph.norm_w != nullptr) {
+          if (warp == 0) {
+            const float sc = rms_scale_smem(xs, M, ph.norm_eps, lane);
+            if (lane == 0) s_bcast = sc;
+          }
+          consumer_sync();
+          const float sc = s_bcast;
+          for (int i = tid; i < M; i += kConsumerThreads)
+            xs[i] = __fmul_rn(__fmul_rn(sc, xs[i]), ph.norm_w[i]);  // rmsnorm_kernel.cu:41-45
+          consumer_sync();
+        }
+      }
+      const float4* xs4 = reinterpret_cast<const float4*>(xs);
+
+      const int u0 = static_cast<int>(static_cast<long long>(cta) * ph.units / G);
+      const int u1 = static_cast<int>(static_cast<long long>(cta + 1) * ph.units / G);
+      const int rpu = ph.swiglu ? 2 : 1;
+      const int row_bytes = M * wbytes;
+      const float* residual = ph.residual_from_emb ? emb_row : ph.residual;
+
+      auto epilogue = [&](int unit, float d0, float d1) {
+        // lane 0 only
+        if (ph.swiglu) {
+          ph.seg[0].out[unit] = swiglu_ref(d0, d1);
+          return;
+        }
+        const RowRef rr = resolve_row(ph, unit, 0);
+        float v = d0;
+        if (ph.seg[rr.seg].bias != nullptr) v = __fadd_rn(v, ph.seg[rr.seg].bias[rr.row]);
+        if (residual != nullptr) v = __fadd_rn(__ldcg(residual + rr.row), v);
+        ph.seg[rr.seg].out[static_cast<long long>(pos) * ph.seg[rr.seg].pos_stride + rr.row] = v;
+        if (ph.argmax) arg_fold(best, v, rr.row);
+      };
+
+      if (ph.chunks_per_row == 1) {
+        const int ups = ph.rows_per_stage / rpu;
+        for (int u = u0; u < u1; u += ups) {
+          const int n = min(ups, u1 - u);
+          mbar_wait(&full_bar[pipe.slot], pipe.parity);
+          const unsigned char* sbase = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
+          for (int i = warp; i < n; i += kConsumerWarps) {
+            const int unit = u + i;
+            if (P.group_size == 0) {
+              if (ph.swiglu) {
+                const float4* w[2] = {reinterpret_cast<const float4*>(sbase + static_cast<size_t>(2 * i) * row_bytes),
+                                      reinterpret_cast<const float4*>(sbase + static_cast<size_t>(2 * i + 1) * row_bytes)};
+                float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                accum_f32<2>(w, xs4, M >> 2, lane, acc);
+                const float d0 = block128_sum_vt(acc[0]);
+                const float d1 = block128_sum_vt(acc[1]);
+                if (lane == 0) epilogue(unit, d0, d1);
+              } else {
+                const float4* w[1] = {reinterpret_cast<const float4*>(sbase + static_cast<size_t>(i) * row_bytes)};
+                float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+                accum_f32<1>(w, xs4, M >> 2, lane, acc);
+                const float d0 = block128_sum_vt(acc[0]);
+                if (lane == 0) epilogue(unit, d0, 0.f);
+              }
+            } else {
+              if (ph.swiglu) {
+                const uint32_t* w[2];
+                const float* sc[2];
+                long long eb[2];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                  w[r] = reinterpret_cast<const uint32_t*>(sbase + static_cast<size_t>(2 * i + r) * row_bytes);
+                  sc[r] = reinterpret_cast<const float*>(sbase + ph.scale_off +
+                                                         static_cast<size_t>(2 * i + r) * ph.scale_row_bytes);
+                  eb[r] = static_cast<long long>(unit) * M;
+                }
+                float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                accum_w8<2>(w, sc, eb, xs4, M, ph.group_shift, ph.group_size, lane, acc);
+                const float d0 = block128_sum_quad(acc[0]);
+                const float d1 = block128_sum_quad(acc[1]);
+                if (lane == 0) epilogue(unit, d0, d1);
+              } else {
+                const RowRef rr = resolve_row(ph, unit, 0);
+                const uint32_t* w[1] = {reinterpret_cast<const uint32_t*>(sbase + static_cast<size_t>(i) * row_bytes)};
+                const float* sc[1] = {reinterpret_cast<const float*>(sbase + ph.scale_off +
+                                                                     static_cast<size_t>(i) * ph.scale_row_bytes)};
+                const long long eb[1] = {static_cast<long long>(rr.row) * M};
+                float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+                accum_w8<1>(w, sc, eb, xs4, M, ph.group_shift, ph.group_size, lane, acc);
+                const float d0 = block128_sum_quad(acc[0]);
+                if (lane == 0) epilogue(unit, d0, 0.f);
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
+          pipe.advance(S);
+        }
+      } else {
+        // rows longer than a stage (fp32 only): the owning warp carries its partial sums across
+        // consecutive stages; chunk boundaries are multiples of 128 packs so every virtual
+        // thread still sees its packs in increasing order.
+        for (int u = u0; u < u1; ++u) {
+          const bool mine = ((u - u0) % kConsumerWarps) == warp;
+          float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+          for (int c = 0; c < ph.chunks_per_row; ++c) {
+            const int e0 = c * ph.chunk_elems;
+            const int ne = min(ph.chunk_elems, M - e0);
+            mbar_wait(&full_bar[pipe.slot], pipe.parity);
+            if (mine) {
+              const float4* w[1] = {reinterpret_cast<const float4*>(
+                  stages + static_cast<size_t>(pipe.slot) * P.stage_bytes)};
+              accum_f32<1>(w, xs4 + (e0 >> 2), ne >> 2, lane, acc);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
+            pipe.advance(S);
+          }
+          if (mine) {
+            const float d0 = block128_sum_vt(acc[0]);
+            if (lane == 0) epilogue(u, d0, 0.f);
+          }
+        }
+      }
+
+      if (ph.argmax) {
+        // per-CTA (max, lowest index) of the classifier rows this CTA produced
+        float bv = __shfl_sync(kFull, best.v, 0);
+        int bi = __shfl_sync(kFull, best.i, 0);
+        if (lane == 0) {
+          s_argv[warp] = bv;
+          s_argi[warp] = bi;
+        }
+        consumer_sync();
+        if (tid == 0) {
+          ArgBest b{0.f, -1};
+          for (int w = 0; w < kConsumerWarps; ++w) arg_fold(b, s_argv[w], s_argi[w]);
+          P.arg_val[cta] = b.v;
+          P.arg_idx[cta] = b.i;
+        }
+      }
+      grid_barrier(P.barrier, bar_target, G);
+    }
+
+    // ---- greedy id: every CTA folds the per-CTA partials identically (argmax_kernel.cu:49-71
+    // semantics: maximum value, lowest index) -------------------------------------------------------
+    ArgBest b{0.f, -1};
+    for (int c = lane; c < G; c += 32) arg_fold(b, __ldcg(P.arg_val + c), __ldcg(P.arg_idx + c));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1)
+      arg_fold(b, __shfl_xor_sync(kFull, b.v, off), __shfl_xor_sync(kFull, b.i, off));
+    const int next = b.i < 0 ? 0 : b.i;
+    if (cta == 0 && tid == 0) {
+      if (P.out_tokens != nullptr && step < P.max_steps) P.out_tokens[step] = next;
+    }
+    token = (P.teacher != nullptr && step + 1 < P.max_steps) ? P.teacher[step + 1] : next;
+    if (static_cast<unsigned>(token) >= static_cast<unsigned>(P.vocab_size)) token = 0;
+    pos += 1;
+    step += 1;
+    if (cta == 0 && tid == 0 && tok == P.n_tokens - 1) {
+      P.state->token = token;
+      P.state->pos = pos;
+      P.state->step = step;
+      P.state->next = next;
+    }
+  }
+}
+
+}  // namespace mega
+
+// ================================== host side ======================================================
+using mega::Params;
+using mega::Phase;
+
+int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
+  model_ = m;
+  stream_ = stream;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return KLLM_E_NODEVICE;
+  int sms = 0, coop = 0, max_smem = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (!coop) return KLLM_E_UNSUPPORTED;
+  grid_ = sms;
+
+  const int dim = m.dim, hid = m.hidden_dim, hs = m.head_size, kvd = m.kv_dim;
+  const int q_rows = m.head_num * hs;
+  const bool int8 = m.group_size > 0;
+  const int wb = int8 ? 1 : 4;
+  // shapes the ring handles: 16-byte rows, 128-byte aligned kv rows (L1-cached reads stay exact)
+  if ((dim & 3) || (hid & 3) || (q_rows & 3) || (hs & 3) || hs > mega::kConsumerThreads) return KLLM_E_UNSUPPORTED;
+  if (int8 && ((dim & 15) || (hid & 15) || (q_rows & 15) || (m.group_size & 3))) return KLLM_E_UNSUPPORTED;
+  if ((kvd * 4) % 128 != 0) return KLLM_E_UNSUPPORTED;
+  if (int8) {
+    const int dims[3] = {dim, hid, q_rows};
+    for (int d : dims)
+      if (d % m.group_size != 0 || ((d / m.group_size) * 4) % 16 != 0) return KLLM_E_UNSUPPORTED;
+  }
+
+  // ---- shared memory plan -----------------------------------------------------------------------
+  const int max_in = std::max(std::max(dim, hid), q_rows);
+  int xbuf = max_in * 4;
+  const int attn_ws = (2 * hs + 2 * mega::kVTile * hs) * 4;
+  xbuf = std::max(xbuf, attn_ws);
+  xbuf = (xbuf + 127) & ~127;
+  const int budget = max_smem - xbuf - 2048;  // static smem + slack
+  const int min_row = std::min(std::min(dim, hid), q_rows) * wb;
+  (void)min_row;
+  int stage_bytes = 32 * 1024;
+  if (const char* e = getenv("KLLM_STAGE_BYTES")) stage_bytes = atoi(e);
+  stage_bytes = (stage_bytes + 127) & ~127;
+  int stages = budget / stage_bytes;
+  if (stages > mega::kMaxStages) stages = mega::kMaxStages;
+  if (const char* e = getenv("KLLM_STAGES")) stages = std::min(stages, atoi(e));
+  if (stages < 2) return KLLM_E_UNSUPPORTED;
+  stage_bytes_ = stage_bytes;
+  stages_ = stages;
+  xbuf_bytes_ = xbuf;
+  smem_bytes_ = static_cast<size_t>(xbuf) + static_cast<size_t>(stages) * stage_bytes;
+
+  // ---- phase table ---------------------------------------------------------------------------------
+  std::vector<Phase> ph;
+  auto plan = [&](Phase& p) -> int {
+    const int row_bytes = p.in_dim * wb;
+    p.group_size = m.group_size;
+    p.group_shift = -1;
+    if (int8 && (m.group_size & (m.group_size - 1)) == 0) {
+      int s = 0;
+      while ((1 << s) < m.group_size) ++s;
+      p.group_shift = s;
+    }
+    p.scale_row_bytes = int8 ? (p.in_dim / m.group_size) * 4 : 0;
+    const int rpu = p.swiglu ? 2 : 1;
+    const int per_row = row_bytes + p.scale_row_bytes;
+    if (per_row * rpu <= stage_bytes) {
+      int rows = stage_bytes / per_row;
+      rows -= rows % rpu;
+      rows = std::min(rows, 32);  // one bulk copy per producer lane
+      p.rows_per_stage = rows;
+      p.chunks_per_row = 1;
+      p.chunk_elems = p.in_dim;
+      p.scale_off = ((rows * row_bytes) + 127) & ~127;
+      if (p.scale_off + rows * p.scale_row_bytes > stage_bytes) {
+        // shrink until weights + scales fit
+        while (rows > rpu && (((rows * row_bytes + 127) & ~127) + rows * p.scale_row_bytes) > stage_bytes)
+          rows -= rpu;
+        p.rows_per_stage = rows;
+        p.scale_off = ((rows * row_bytes) + 127) & ~127;
+      }
+    } else {
+      if (int8 || p.swiglu) return KLLM_E_UNSUPPORTED;
+      const int chunk_max = (stage_bytes / 4) & ~511;  // multiple of 128 packs
+      p.chunks_per_row = (p.in_dim + chunk_max - 1) / chunk_max;
+      int ce = (p.in_dim + p.chunks_per_row - 1) / p.chunks_per_row;
+      ce = (ce + 511) & ~511;
+      p.chunk_elems = ce;
+      p.chunks_per_row = (p.in_dim + ce - 1) / ce;
+      p.rows_per_stage = 1;
+      p.scale_off = 0;
+    }
+    return 0;
+  };
+
+  const float eps = flavour_eps(m.flavour);
+  for (int l = 0; l < m.layer_num; ++l) {
+    const size_t layer_off = static_cast<size_t>(l) * m.seq_len * kvd;
+    {  // attention_rms + q | k | v (+bias).  k goes to k_raw (rotated later), v into the cache.
+      Phase p{};
+      p.kind = mega::kPhaseGemv;
+      p.in_dim = dim;
+      p.n_seg = 3;
+      p.x = m.x;
+      p.x_from_emb = (l == 0);
+      p.norm_w = m.attn_norm[l];
+      p.norm_eps = eps;
+      p.seg[0] = {m.wq[l], int8 ? m.sq[l] : nullptr, m.bq ? m.bq[l] : nullptr, m.q, 0, q_rows};
+      p.seg[1] = {m.wk[l], int8 ? m.sk[l] : nullptr, m.bk ? m.bk[l] : nullptr, m.k_raw, 0, kvd};
+      p.seg[2] = {m.wv[l], int8 ? m.sv[l] : nullptr, m.bv ? m.bv[l] : nullptr,
+                  m.value_cache + layer_off, kvd, kvd};
+      p.units = q_rows + 2 * kvd;
+      if (int rc = plan(p)) return rc;
+      ph.push_back(p);
+    }
+    {
+      Phase p{};
+      p.kind = mega::kPhaseAttention;
+      p.layer = l;
+      ph.push_back(p);
+    }
+    {  // wo + residual (llama3.cpp:672-684)
+      Phase p{};
+      p.kind = mega::kPhaseGemv;
+      p.in_dim = q_rows;
+      p.n_seg = 1;
+      p.x = m.attn_out;
+      p.seg[0] = {m.wo[l], int8 ? m.so[l] : nullptr, nullptr, m.x, 0, dim};
+      p.residual = m.x;
+      p.residual_from_emb = (l == 0);
+      p.units = dim;
+      if (int rc = plan(p)) return rc;
+      ph.push_back(p);
+    }
+    {  // ffn rmsnorm + w1 | w3 -> swiglu (llama3.cpp:686-708)
+      Phase p{};
+      p.kind = mega::kPhaseGemv;
+      p.in_dim = dim;
+      p.n_seg = 2;
+      p.swiglu = 1;
+      p.x = m.x;
+      p.norm_w = m.ffn_norm[l];
+      p.norm_eps = eps;
+      p.seg[0] = {m.w1[l], int8 ? m.s1[l] : nullptr, nullptr, m.h, 0, hid};
+      p.seg[1] = {m.w3[l], int8 ? m.s3[l] : nullptr, nullptr, nullptr, 0, hid};
+      p.units = hid;
+      if (int rc = plan(p)) return rc;
+      ph.push_back(p);
+    }
+    {  // w2 + residual (llama3.cpp:711-719)
+      Phase p{};
+      p.kind = mega::kPhaseGemv;
+      p.in_dim = hid;
+      p.n_seg = 1;
+      p.x = m.h;
+      p.seg[0] = {m.w2[l], int8 ? m.s2[l] : nullptr, nullptr, m.x, 0, dim};
+      p.residual = m.x;
+      p.units = dim;
+      if (int rc = plan(p)) return rc;
+      ph.push_back(p);
+    }
+  }
+  {  // final rmsnorm + classifier (+ argmax partials)
+    Phase p{};
+    p.kind = mega::kPhaseGemv;
+    p.in_dim = dim;
+    p.n_seg = 1;
+    p.x = m.x;
+    p.norm_w = m.final_norm;
+    p.norm_eps = eps;
+    p.seg[0] = {m.wcls, int8 ? m.scls : nullptr, nullptr, m.logits, 0, m.vocab_size};
+    p.units = m.vocab_size;
+    p.argmax = 1;
+    if (int rc = plan(p)) return rc;
+    ph.push_back(p);
+  }
+  n_phases_ = static_cast<int>(ph.size());
+  n_barriers_per_token_ = n_phases_;
+
+  if (cudaMalloc(&d_phases_, sizeof(Phase) * ph.size()) != cudaSuccess) return static_cast<int>(cudaErrorMemoryAllocation);
+  cudaMemcpyAsync(d_phases_, ph.data(), sizeof(Phase) * ph.size(), cudaMemcpyHostToDevice, stream);
+  if (cudaMalloc(&d_barrier_, 128) != cudaSuccess) return static_cast<int>(cudaErrorMemoryAllocation);
+  cudaMemsetAsync(d_barrier_, 0, 128, stream);
+  if (cudaMalloc(&d_arg_val_, sizeof(float) * grid_) != cudaSuccess ||
+      cudaMalloc(&d_arg_idx_, sizeof(int) * grid_) != cudaSuccess)
+    return static_cast<int>(cudaErrorMemoryAllocation);
+  cudaStreamSynchronize(stream);  // ph (host vector) must outlive the async copy
+
+  cudaError_t e = cudaFuncSetAttribute(mega::decode_megakernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem_bytes_));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mega::decode_megakernel, mega::kThreads,
+                                                    smem_bytes_);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (occ < 1) return KLLM_E_UNSUPPORTED;
+  barrier_base_ = 0;
+  ready_ = true;
+  return 0;
+}
+
+void MegaEngine::destroy() {
+  if (d_phases_) cudaFree(d_phases_);
+  if (d_barrier_) cudaFree(d_barrier_);
+  if (d_arg_val_) cudaFree(d_arg_val_);
+  if (d_arg_idx_) cudaFree(d_arg_idx_);
+  d_phases_ = nullptr;
+  d_barrier_ = nullptr;
+  d_arg_val_ = nullptr;
+  d_arg_idx_ = nullptr;
+  ready_ = false;
+}
+
+int MegaEngine::run(int n_tokens, const int32_t* teacher_dev) {
+  if (!ready_) return KLLM_E_STATE;
+  Params P{};
+  const MegaModel& m = model_;
+  P.phases = static_cast<const Phase*>(d_phases_);
+  P.n_phases = n_phases_;
+  P.n_tokens = n_tokens;
+  P.num_stages = stages_;
+  P.stage_bytes = stage_bytes_;
+  P.xbuf_bytes = xbuf_bytes_;
+  P.group_size = m.group_size;
+  P.dim = m.dim;
+  P.vocab_size = m.vocab_size;
+  P.head_num = m.head_num;
+  P.head_size = m.head_size;
+  P.kv_dim = m.kv_dim;
+  P.kv_mul = m.kv_mul;
+  P.seq_len = m.seq_len;
+  P.flavour = m.flavour;
+  P.tok_emb = m.tok_emb;
+  P.q = m.q;
+  P.k_raw = m.k_raw;
+  P.attn_out = m.attn_out;
+  P.score = m.score;
+  P.key_cache = m.key_cache;
+  P.value_cache = m.value_cache;
+  P.sin_cache = m.sin_cache;
+  P.cos_cache = m.cos_cache;
+  P.state = static_cast<mega::State*>(m.state);
+  P.out_tokens = m.out_tokens;
+  P.teacher = teacher_dev;
+  P.max_steps = m.seq_len;
+  P.barrier = static_cast<unsigned*>(d_barrier_);
+  P.barrier_base = barrier_base_;
+  P.arg_val = static_cast<float*>(d_arg_val_);
+  P.arg_idx = static_cast<int*>(d_arg_idx_);
+  void* args[] = {&P};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mega::decode_megakernel),
+                                              dim3(grid_), dim3(mega::kThreads), args, smem_bytes_,
+                                              stream_);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  barrier_base_ += static_cast<unsigned>(n_tokens) * static_cast<unsigned>(n_barriers_per_token_) *
+                   static_cast<unsigned>(grid_);
+  count_launch();
+  return 0;
+}
+
+}  // namespace kllm

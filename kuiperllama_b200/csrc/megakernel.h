@@ -1,0 +1,127 @@
+// Host/device shared declarations of the persistent decode megakernel (megakernel.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+namespace kllm {
+namespace mega {
+
+enum { kPhaseGemv = 0, kPhaseAttention = 1 };
+
+struct Seg {
+  const void* w;        // fp32 or int8 [rows, in_dim]
+  const float* scales;  // int8 only
+  const float* bias;    // optional
+  float* out;           // out[pos * pos_stride + row]
+  long long pos_stride;
+  int rows;
+};
+
+// One entry of the per-token schedule.  A GEMV phase's units (rows, or w1/w3 row pairs) are
+// split evenly over the CTAs; each CTA streams its contiguous share through the stage ring.
+struct Phase {
+  int kind;
+  int in_dim;
+  int units;
+  int n_seg;
+  int swiglu;             // units are (w1 row, w3 row) pairs -> SiLU*gate epilogue
+  int argmax;             // track (max, index) of the produced rows (classifier)
+  int x_from_emb;         // input vector is the embedding row of the current token
+  int residual_from_emb;  // residual source is the embedding row (layer 0)
+  int group_size, group_shift;
+  int rows_per_stage;     // whole rows per ring stage (chunks_per_row == 1)
+  int chunks_per_row;     // > 1: a row spans this many stages (fp32 rows longer than a stage)
+  int chunk_elems;
+  int scale_off;          // byte offset of the scales region inside a stage (int8)
+  int scale_row_bytes;
+  int layer;              // attention: layer index
+  float norm_eps;
+  const float* x;         // input vector (global memory)
+  const float* norm_w;    // optional RMSNorm weight applied to x
+  const float* residual;  // optional residual vector
+  Seg seg[3];
+};
+
+struct State {  // == StepState in decoder.cu
+  int32_t token, pos, step, next;
+};
+
+struct Params {
+  const Phase* phases;
+  int n_phases, n_tokens;
+  int num_stages, stage_bytes, xbuf_bytes;
+  int group_size;
+  int dim, vocab_size, head_num, head_size, kv_dim, kv_mul, seq_len, flavour;
+  const float* tok_emb;
+  const float* q;
+  const float* k_raw;
+  float* attn_out;
+  float* score;
+  float* key_cache;
+  const float* value_cache;
+  const float* sin_cache;
+  const float* cos_cache;
+  State* state;
+  int32_t* out_tokens;
+  const int32_t* teacher;
+  int max_steps;
+  unsigned* barrier;
+  unsigned barrier_base;
+  float* arg_val;
+  int* arg_idx;
+};
+
+}  // namespace mega
+
+// Everything the engine needs to know about the model; all pointers are device pointers, the
+// per-layer arrays are host arrays of device pointers (owned by the decoder).
+struct MegaModel {
+  int dim, hidden_dim, layer_num, head_num, kv_head_num, vocab_size, seq_len;
+  int head_size, kv_dim, kv_mul, flavour, group_size;
+  const float* tok_emb;
+  const float* const* attn_norm;
+  const float* const* ffn_norm;
+  const float* final_norm;
+  const void* const* wq; const void* const* wk; const void* const* wv; const void* const* wo;
+  const void* const* w1; const void* const* w2; const void* const* w3;
+  const void* wcls;
+  const float* const* sq; const float* const* sk; const float* const* sv; const float* const* so;
+  const float* const* s1; const float* const* s2; const float* const* s3;
+  const float* scls;
+  const float* const* bq; const float* const* bk; const float* const* bv;
+  // activations / state owned by the decoder
+  float* x; float* q; float* k_raw; float* attn_out; float* h; float* logits; float* score;
+  float* key_cache; float* value_cache;
+  const float* sin_cache; const float* cos_cache;
+  void* state;
+  int32_t* out_tokens;
+};
+
+class MegaEngine {
+ public:
+  int init(const MegaModel& m, cudaStream_t stream);
+  void destroy();
+  // Run n_tokens consecutive positions starting from the device-resident state.
+  int run(int n_tokens, const int32_t* teacher_dev);
+  bool ready() const { return ready_; }
+  int stages() const { return stages_; }
+  int stage_bytes() const { return stage_bytes_; }
+  int phases() const { return n_phases_; }
+
+ private:
+  MegaModel model_{};
+  cudaStream_t stream_ = nullptr;
+  void* d_phases_ = nullptr;
+  void* d_barrier_ = nullptr;
+  void* d_arg_val_ = nullptr;
+  void* d_arg_idx_ = nullptr;
+  int grid_ = 0, stages_ = 0, stage_bytes_ = 0, xbuf_bytes_ = 0, n_phases_ = 0;
+  int n_barriers_per_token_ = 0;
+  size_t smem_bytes_ = 0;
+  unsigned barrier_base_ = 0;
+  bool ready_ = false;
+};
+
+}  // namespace kllm

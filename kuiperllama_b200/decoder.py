@@ -195,6 +195,10 @@ class Decoder:
     def launches_per_step(self) -> int:
         return self.lib.kllm_decoder_launches_per_step(self.handle)
 
+    @property
+    def engine(self) -> str:
+        return self.lib.kllm_decoder_engine(self.handle).decode()
+
     def step(self, token: int, pos: int, is_prompt: bool = False) -> int:
         """Reference-facing call with host buffers (predict + post_processing)."""
         nxt = ctypes.c_int32(-1)

@@ -18,6 +18,14 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-4  # BASELINE.json north_star: logits within 1e-4 fp32
 
 
+@pytest.fixture(autouse=True, params=["persistent", "graph"])
+def engine(request, monkeypatch):
+    """Every decoder test runs on both engines: the persistent megakernel (TMA weight ring, one
+    cooperative launch) and the CUDA-graph chain of fused launches."""
+    monkeypatch.setenv("KLLM_ENGINE", request.param)
+    return request.param
+
+
 def load_decoder(path, quant=False, flavour="llama2", qkv_bias=None):
     from kuiperllama_b200 import Decoder
     from kuiperllama_b200.checkpoint import read_checkpoint, to_device
@@ -141,7 +149,7 @@ def test_qwen2_flavour_vs_cpu_oracle(kllm_lib, oracle, tmp_path):
     om.close(); dec.close()
 
 
-def test_teacher_forced_generate_and_determinism(kllm_lib):
+def test_teacher_forced_generate_and_determinism(kllm_lib, engine):
     from kuiperllama_b200 import SHAPES, Decoder, synth_weights
     shape = SHAPES["small"]
     dec = Decoder(shape, synth_weights(shape, "cuda", 11))
@@ -151,7 +159,8 @@ def test_teacher_forced_generate_and_determinism(kllm_lib):
     inputs = [1] + free[:-1]
     forced = dec.generate(0, 0, 100, teacher=inputs)
     assert forced == free
-    assert dec.launches_per_step == 6 * shape.layer_num + 3
+    assert dec.engine == engine
+    assert dec.launches_per_step == (1 if engine == "persistent" else 6 * shape.layer_num + 3)
     dec.close()
 
 
