@@ -190,6 +190,13 @@ int kllm_decoder_launches_per_step(const kllm_decoder* dec);
  * ring; "graph": CUDA-graph chain of fused launches (shapes the ring does not handle, tensor
  * parallel).  Environment KLLM_ENGINE=graph|persistent forces a choice at create time. */
 const char* kllm_decoder_engine(const kllm_decoder* dec);
+/* Persistent engine only: run n_steps positions and record, for step `profiled_step`, four
+ * globaltimer stamps (ns) per CTA per schedule phase -- phase entered / input vector staged /
+ * last ring stage consumed / grid barrier passed -- into stamps_host[grid][phases][4]
+ * (capacity in uint64 elements).  Measurement aid (profiles/), not part of the decode path. */
+int kllm_decoder_profile(kllm_decoder* dec, int32_t first_token, int32_t start_pos,
+                         int32_t n_steps, int32_t profiled_step, uint64_t* stamps_host,
+                         int32_t capacity, int32_t* grid_out, int32_t* phases_out);
 
 #ifdef __cplusplus
 }

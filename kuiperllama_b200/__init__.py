@@ -91,6 +91,8 @@ _SIGNATURES = {
     "kllm_decoder_value_cache": (c_void_p, [c_void_p]),
     "kllm_decoder_launches_per_step": (c_int, [c_void_p]),
     "kllm_decoder_engine": (c_char_p, [c_void_p]),
+    "kllm_decoder_profile": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
+                                     POINTER(c_int32), POINTER(c_int32)]),
 }
 
 _lib = None

@@ -464,6 +464,32 @@ int kllm_decoder_generate(kllm_decoder* dc, int32_t first_token, int32_t start_p
   return 0;
 }
 
+int kllm_decoder_profile(kllm_decoder* dc, int32_t first_token, int32_t start_pos, int32_t n_steps,
+                         int32_t profiled_step, uint64_t* stamps_host, int32_t capacity,
+                         int32_t* grid_out, int32_t* phases_out) {
+  if (!dc || !stamps_host || !grid_out || !phases_out || n_steps <= 0) return KLLM_E_INVALID;
+  if (!dc->use_mega) return KLLM_E_UNSUPPORTED;
+  if (start_pos < 0 || start_pos + n_steps > dc->d.seq_len) return KLLM_E_INVALID;
+  const int grid = dc->mega.grid(), phases = dc->mega.phases();
+  const size_t n = static_cast<size_t>(grid) * phases * 4;
+  *grid_out = grid;
+  *phases_out = phases;
+  if (static_cast<size_t>(capacity) < n) return KLLM_E_INVALID;
+  unsigned long long* d_prof = nullptr;
+  KLLM_TRY(cudaMalloc(&d_prof, n * sizeof(unsigned long long)));
+  cudaMemsetAsync(d_prof, 0, n * sizeof(unsigned long long), dc->stream);
+  StepState* hs = dc->st_host;
+  hs->token = first_token, hs->pos = start_pos, hs->step = 0, hs->next = -1;
+  cudaMemcpyAsync(dc->st, hs, sizeof(StepState), cudaMemcpyHostToDevice, dc->stream);
+  int rc = dc->mega.run(n_steps, nullptr, d_prof, profiled_step);
+  if (rc == 0) rc = static_cast<int>(cudaStreamSynchronize(dc->stream));
+  if (rc == 0)
+    rc = static_cast<int>(cudaMemcpy(stamps_host, d_prof, n * sizeof(unsigned long long),
+                                     cudaMemcpyDeviceToHost));
+  cudaFree(d_prof);
+  return rc;
+}
+
 int kllm_decoder_logits(kllm_decoder* dc, float* logits_host) {
   if (!dc || !logits_host) return KLLM_E_INVALID;
   KLLM_TRY(cudaStreamSynchronize(dc->stream));

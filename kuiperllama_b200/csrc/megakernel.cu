@@ -91,6 +91,12 @@ __device__ __forceinline__ void consumer_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct Pipe {
   int slot;
   uint32_t parity;
@@ -449,12 +455,18 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
     const float* emb_row = P.tok_emb + static_cast<size_t>(token) * P.dim;
     ArgBest best{0.f, -1};
 
+    const bool prof_on = P.prof != nullptr && tok == P.prof_token && tid == 0;
     for (int pi = 0; pi < P.n_phases; ++pi) {
       const Phase& ph = P.phases[pi];
+      unsigned long long* stamp =
+          prof_on ? P.prof + (static_cast<size_t>(cta) * P.n_phases + pi) * 4 : nullptr;
+      if (stamp) stamp[0] = global_ns();
 
       if (ph.kind == kPhaseAttention) {
         if (cta < P.head_num) attention_phase(P, ph, cta, pos, xs, s_warp, &s_bcast);
+        if (stamp) stamp[1] = stamp[2] = global_ns();
         grid_barrier(P.barrier, bar_target, G);
+        if (stamp) stamp[3] = global_ns();
         continue;
       }
 
@@ -479,6 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
         }
       }
       const float4* xs4 = reinterpret_cast<const float4*>(xs);
+      if (stamp) stamp[1] = global_ns();
 
       const int u0 = static_cast<int>(static_cast<long long>(cta) * ph.units / G);
       const int u1 = static_cast<int>(static_cast<long long>(cta + 1) * ph.units / G);
@@ -506,7 +519,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
           const int n = min(ups, u1 - u);
           mbar_wait(&full_bar[pipe.slot], pipe.parity);
           const unsigned char* sbase = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
-          for (int i = warp; i < n; i += kConsumerWarps) {
+          // units go round-robin over ALL consumer warps across stages (a stage may hold fewer
+          // units than there are warps)
+          const int first = ((warp - (u - u0)) % kConsumerWarps + kConsumerWarps) % kConsumerWarps;
+          for (int i = first; i < n; i += kConsumerWarps) {
             const int unit = u + i;
             if (P.group_size == 0) {
               if (ph.swiglu) {
@@ -601,7 +617,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
           P.arg_idx[cta] = b.i;
         }
       }
+      if (stamp) stamp[2] = global_ns();
       grid_barrier(P.barrier, bar_target, G);
+      if (stamp) stamp[3] = global_ns();
     }
 
     // ---- greedy id: every CTA folds the per-CTA partials identically (argmax_kernel.cu:49-71
@@ -843,7 +861,8 @@ void MegaEngine::destroy() {
   ready_ = false;
 }
 
-int MegaEngine::run(int n_tokens, const int32_t* teacher_dev) {
+int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long* prof_dev,
+                    int prof_token) {
   if (!ready_) return KLLM_E_STATE;
   Params P{};
   const MegaModel& m = model_;
@@ -879,6 +898,8 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev) {
   P.barrier_base = barrier_base_;
   P.arg_val = static_cast<float*>(d_arg_val_);
   P.arg_idx = static_cast<int*>(d_arg_idx_);
+  P.prof = prof_dev;
+  P.prof_token = prof_token;
   void* args[] = {&P};
   cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mega::decode_megakernel),
                                               dim3(grid_), dim3(mega::kThreads), args, smem_bytes_,

@@ -71,6 +71,10 @@ struct Params {
   unsigned barrier_base;
   float* arg_val;
   int* arg_idx;
+  // optional phase timeline of one token: prof[(cta * n_phases + phase) * 4 + k], k = phase
+  // entered / input staged / last stage consumed / grid barrier passed (globaltimer ns)
+  unsigned long long* prof;
+  int prof_token;
 };
 
 }  // namespace mega
@@ -104,7 +108,9 @@ class MegaEngine {
   int init(const MegaModel& m, cudaStream_t stream);
   void destroy();
   // Run n_tokens consecutive positions starting from the device-resident state.
-  int run(int n_tokens, const int32_t* teacher_dev);
+  int run(int n_tokens, const int32_t* teacher_dev, unsigned long long* prof_dev = nullptr,
+          int prof_token = -1);
+  int grid() const { return grid_; }
   bool ready() const { return ready_; }
   int stages() const { return stages_; }
   int stage_bytes() const { return stage_bytes_; }
