@@ -180,20 +180,21 @@ int kllm_decoder_generate(kllm_decoder* dec, int32_t first_token, int32_t start_
                           int32_t n_steps, const int32_t* teacher_host,
                           int32_t* out_tokens_host);
 
-/* Blocking copies for tests: logits of the last step [vocab], and raw views. */
+/* Blocking copies for tests: logits of the last step [vocab]; the KV cache in the REFERENCE
+ * layout [layer][seq_len][kv_dim] (llama3.cpp:469-475) whatever the engine keeps internally. */
 int kllm_decoder_logits(kllm_decoder* dec, float* logits_host);
-const float* kllm_decoder_key_cache(kllm_decoder* dec);   /* device [L, seq_len, kv_dim] */
-const float* kllm_decoder_value_cache(kllm_decoder* dec); /* device */
+int kllm_decoder_read_kv(kllm_decoder* dec, float* key_host, float* value_host);
 /* Kernel launches one decode step issues (graph nodes; 1 for the persistent engine). */
 int kllm_decoder_launches_per_step(const kllm_decoder* dec);
 /* "persistent": one cooperative megakernel launch runs whole positions with a TMA-fed weight
  * ring; "graph": CUDA-graph chain of fused launches (shapes the ring does not handle, tensor
  * parallel).  Environment KLLM_ENGINE=graph|persistent forces a choice at create time. */
 const char* kllm_decoder_engine(const kllm_decoder* dec);
-/* Persistent engine only: run n_steps positions and record, for step `profiled_step`, four
- * globaltimer stamps (ns) per CTA per schedule phase -- phase entered / input vector staged /
- * last ring stage consumed / grid barrier passed -- into stamps_host[grid][phases][4]
- * (capacity in uint64 elements).  Measurement aid (profiles/), not part of the decode path. */
+/* Persistent engine only: run n_steps positions and record, for step `profiled_step`, eight
+ * globaltimer stamps (ns) per CTA per schedule phase into stamps_host[grid][phases][8]
+ * (capacity in uint64 elements): [0] phase entered, [1] input vector staged, [2] last ring stage
+ * consumed, [3] grid barrier passed (consumer side); [4] producer warp starts / [5] finishes
+ * issuing the phase's TMA copies; [6],[7] unused.  Measurement aid (profiles/). */
 int kllm_decoder_profile(kllm_decoder* dec, int32_t first_token, int32_t start_pos,
                          int32_t n_steps, int32_t profiled_step, uint64_t* stamps_host,
                          int32_t capacity, int32_t* grid_out, int32_t* phases_out);

@@ -471,7 +471,7 @@ int kllm_decoder_profile(kllm_decoder* dc, int32_t first_token, int32_t start_po
   if (!dc->use_mega) return KLLM_E_UNSUPPORTED;
   if (start_pos < 0 || start_pos + n_steps > dc->d.seq_len) return KLLM_E_INVALID;
   const int grid = dc->mega.grid(), phases = dc->mega.phases();
-  const size_t n = static_cast<size_t>(grid) * phases * 4;
+  const size_t n = static_cast<size_t>(grid) * phases * 8;
   *grid_out = grid;
   *phases_out = phases;
   if (static_cast<size_t>(capacity) < n) return KLLM_E_INVALID;
@@ -497,8 +497,33 @@ int kllm_decoder_logits(kllm_decoder* dc, float* logits_host) {
                                      cudaMemcpyDeviceToHost));
 }
 
-const float* kllm_decoder_key_cache(kllm_decoder* dc) { return dc ? dc->kcache : nullptr; }
-const float* kllm_decoder_value_cache(kllm_decoder* dc) { return dc ? dc->vcache : nullptr; }
+int kllm_decoder_read_kv(kllm_decoder* dc, float* key_host, float* value_host) {
+  if (!dc || !key_host || !value_host) return KLLM_E_INVALID;
+  KLLM_TRY(cudaStreamSynchronize(dc->stream));
+  const size_t L = dc->d.layer_num, S = dc->d.seq_len, kvd = dc->kv_dim, hs = dc->head_size;
+  const size_t n = L * S * kvd;
+  if (!dc->use_mega) {
+    KLLM_TRY(cudaMemcpy(key_host, dc->kcache, n * sizeof(float), cudaMemcpyDeviceToHost));
+    return static_cast<int>(cudaMemcpy(value_host, dc->vcache, n * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  // persistent engine: K [L][kvh][hs/4][S][4], V [L][kvh][S][hs] -> reference [L][S][kv_dim]
+  std::vector<float> kraw(n), vraw(n);
+  KLLM_TRY(cudaMemcpy(kraw.data(), dc->kcache, n * sizeof(float), cudaMemcpyDeviceToHost));
+  KLLM_TRY(cudaMemcpy(vraw.data(), dc->vcache, n * sizeof(float), cudaMemcpyDeviceToHost));
+  const size_t nh = kvd / hs;
+  for (size_t l = 0; l < L; ++l)
+    for (size_t g = 0; g < nh; ++g) {
+      const float* kb = kraw.data() + (l * nh + g) * S * hs;
+      const float* vb = vraw.data() + (l * nh + g) * S * hs;
+      for (size_t t = 0; t < S; ++t)
+        for (size_t i = 0; i < hs; ++i) {
+          const size_t dst = (l * S + t) * kvd + g * hs + i;
+          key_host[dst] = kb[((i >> 2) * S + t) * 4 + (i & 3)];
+          value_host[dst] = vb[t * hs + i];
+        }
+    }
+  return 0;
+}
 int kllm_decoder_launches_per_step(const kllm_decoder* dc) { return dc ? dc->launches_per_step : 0; }
 const char* kllm_decoder_engine(const kllm_decoder* dc) {
   if (!dc) return "";

@@ -41,7 +41,6 @@ constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32;  // + one producer warp
 constexpr int kMaxStages = 16;
-constexpr int kVTile = 32;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -77,6 +76,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -141,13 +145,32 @@ __device__ __forceinline__ RowRef resolve_row(const Phase& ph, int unit, int sub
 
 // ---- exact-order accumulation from shared memory ----------------------------------------------
 // fp32: virtual thread (lane + 32 j) owns packs base + 32 j + lane (matmul_kernel.cu:27-35).
+// Full 128-pack blocks run branch-free with all 4*(1+NR) shared loads issued before the math
+// (two blocks in flight), so the four independent chains per row overlap the LDS latency.
 template <int NR>
 __device__ __forceinline__ void accum_f32(const float4* const (&w)[NR], const float4* x4,
                                           int n_packs, int lane, float (&acc)[NR][4]) {
-  for (int base = 0; base < n_packs; base += 128) {
+  const int full = n_packs & ~127;
+  const float4* xp = x4 + lane;
+#pragma unroll 2
+  for (int base = 0; base < full; base += 128) {
+    float4 xv[4];
+    float4 wv[NR][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xv[j] = xp[base + 32 * j];
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wv[r][j] = w[r][base + 32 * j + lane];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[r][j] = __fadd_rn(dot4_ref(xv[j], wv[r][j]), acc[r][j]);
+  }
+  if (full < n_packs) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int idx = base + 32 * j + lane;
+      const int idx = full + 32 * j + lane;
       if (idx < n_packs) {
         const float4 xv = x4[idx];
 #pragma unroll
@@ -158,33 +181,32 @@ __device__ __forceinline__ void accum_f32(const float4* const (&w)[NR], const fl
 }
 
 // int8: virtual thread (4 lane + e) owns elements 128 k + 4 lane + e (matmul_kernel.cu:70-74).
+// `sc[r]` points at the row's staged scales (first group of the row at index 0; rows start on a
+// group boundary -- checked on the host).
 template <int NR>
 __device__ __forceinline__ void accum_w8(const uint32_t* const (&w)[NR], const float* const (&sc)[NR],
-                                         const long long (&ebase)[NR], const float4* x4, int M,
-                                         int group_shift, int group_size, int lane,
-                                         float (&acc)[NR][4]) {
-  const int chunks = (M + 127) >> 7;
-  for (int k = 0; k < chunks; ++k) {
+                                         const float4* x4, int M, int group_shift, int group_size,
+                                         int lane, float (&acc)[NR][4]) {
+  const int full_chunks = M >> 7;
+  auto one = [&](int k) {
     const int i = (k << 7) + (lane << 2);
-    if (i < M) {
-      const float4 xv = x4[i >> 2];
+    const float4 xv = x4[i >> 2];
+    const int g = group_shift >= 0 ? (i >> group_shift) : (i / group_size);
 #pragma unroll
-      for (int r = 0; r < NR; ++r) {
-        const uint32_t packed = w[r][i >> 2];
-        // scales of this row staged from the first group the row touches
-        const long long e = ebase[r] + i;
-        const long long g0 = group_shift >= 0 ? (ebase[r] >> group_shift) : (ebase[r] / group_size);
-        const long long g = group_shift >= 0 ? (e >> group_shift) : (e / group_size);
-        const float s = sc[r][g - g0];
-        float wf[4];
-        int8x4_to_float(packed, wf);
-        acc[r][0] = __fmaf_rn(__fmul_rn(xv.x, s), wf[0], acc[r][0]);
-        acc[r][1] = __fmaf_rn(__fmul_rn(xv.y, s), wf[1], acc[r][1]);
-        acc[r][2] = __fmaf_rn(__fmul_rn(xv.z, s), wf[2], acc[r][2]);
-        acc[r][3] = __fmaf_rn(__fmul_rn(xv.w, s), wf[3], acc[r][3]);
-      }
+    for (int r = 0; r < NR; ++r) {
+      const uint32_t packed = w[r][i >> 2];
+      const float s = sc[r][g];
+      float wf[4];
+      int8x4_to_float(packed, wf);
+      acc[r][0] = __fmaf_rn(__fmul_rn(xv.x, s), wf[0], acc[r][0]);
+      acc[r][1] = __fmaf_rn(__fmul_rn(xv.y, s), wf[1], acc[r][1]);
+      acc[r][2] = __fmaf_rn(__fmul_rn(xv.z, s), wf[2], acc[r][2]);
+      acc[r][3] = __fmaf_rn(__fmul_rn(xv.w, s), wf[3], acc[r][3]);
     }
-  }
+  };
+#pragma unroll 4
+  for (int k = 0; k < full_chunks; ++k) one(k);
+  if ((full_chunks << 7) + (lane << 2) < M) one(full_chunks);
 }
 
 // rmsnorm_kernel.cu:4-50 on x staged in shared memory (warp 0), cf. gemv.cu rms_scale_ref.
@@ -192,10 +214,26 @@ __device__ __forceinline__ float rms_scale_smem(const float* xs, int n, float ep
   const int pack_num = n >> 2;
   const float4* xs4 = reinterpret_cast<const float4*>(xs);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int base = 0; base < pack_num; base += 128) {
+  const int full = pack_num & ~127;
+#pragma unroll 2
+  for (int base = 0; base < full; base += 128) {
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = xs4[base + 32 * j + lane];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int idx = base + 32 * j + lane;
+      float s = acc[j];
+      s = __fmaf_rn(v[j].x, v[j].x, s);
+      s = __fmaf_rn(v[j].y, v[j].y, s);
+      s = __fmaf_rn(v[j].z, v[j].z, s);
+      s = __fmaf_rn(v[j].w, v[j].w, s);
+      acc[j] = s;
+    }
+  }
+  if (full < pack_num) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = full + 32 * j + lane;
       if (idx < pack_num) {
         const float4 v = xs4[idx];
         float s = acc[j];
@@ -224,31 +262,49 @@ __device__ __forceinline__ void arg_fold(ArgBest& a, float ov, int oi) {
 }
 
 // ---- attention phase: one CTA per query head (mha_kernel.cu:47-110 + rope_kernel.cu) ------------
-__device__ void attention_phase(const Params& P, const Phase& ph, int head, int pos, float* ws,
-                                float* s_warp, float* s_bcast) {
-  const int tid = threadIdx.x;
-  const int hs = P.head_size, kv_dim = P.kv_dim, seq_len = P.seq_len;
-  float* q_s = ws;             // [hs]
-  float* k_s = ws + hs;        // [hs] rotated key of the current position
-  float* v_s = ws + 2 * hs;    // [2][kVTile][hs]
-  const int kvh = head / P.kv_mul;
-  const int head_offset = kvh * hs;
-  const long long layer_offset = static_cast<long long>(ph.layer) * seq_len * kv_dim;
-  float* kcache = P.key_cache + layer_offset + head_offset;
-  const float* vcache = P.value_cache + layer_offset + head_offset;
-  float* score_head = P.score + static_cast<size_t>(head) * seq_len;
+// KV layout (persistent engine only; kllm_decoder_read_kv converts back):
+//   K [L][kv_head][head_size/4][seq_len][4]   -- 16-byte chunk c of timestep t at ((c*seq_len)+t)*4:
+//       a tile of T timesteps is hs/4 contiguous runs of T*16 bytes, and "thread t reads chunk c"
+//       is a conflict-free 128-bit shared-memory access (consecutive t -> consecutive 16 B);
+//   V [L][kv_head][seq_len][head_size]        -- a tile of T timesteps is one contiguous block and
+//       "thread i walks column i" is conflict-free.
+// Rows t < pos were written by earlier tokens, so -- like weights -- the producer warp streams
+// them through the ring ahead of time (K tiles first, then V tiles); only row pos is handled
+// here from registers / a direct load.
+__device__ __forceinline__ int attn_tiles(int pos, int T) { return (pos + T - 1) / T; }
 
-  // RoPE on q (this head) and on the new key row (this head's kv head), rope_kernel.cu as
-  // compiled (see elementwise.cu): interleaved pairs or half-split pairs.
+__device__ void attention_phase(const Params& P, const Phase& ph, int head, int pos, float* ws,
+                                float* s_warp, float* s_bcast, unsigned char* stages,
+                                uint64_t* full_bar, uint64_t* empty_bar, Pipe& pipe) {
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int hs = P.head_size, seq_len = P.seq_len, T = P.attn_tile, S = P.num_stages;
+  float* q_s = ws;       // [hs] rotated query
+  float* k_s = ws + hs;  // [hs] rotated key of the current position
+  const int kvh = head / P.kv_mul;
+  const size_t head_block = (static_cast<size_t>(ph.layer) * (P.kv_dim / hs) + kvh) * seq_len * hs;
+  float* kcache = P.key_cache + head_block;
+  const float* vcache = P.value_cache + head_block;
+  // scores / probabilities: shared memory when the context fits the workspace (the ring leaves
+  // almost no L1), else the global [head][seq_len] buffer the reference uses
+  const int smem_cap = (P.xbuf_bytes >> 2) - 2 * hs;
+  float* score_head = (pos + 1 <= smem_cap) ? (ws + 2 * hs) : (P.score + static_cast<size_t>(head) * seq_len);
+
+  // value row of the current position (written by the QKV phase of this token)
+  float v_pos = 0.f;
+  if (tid < hs) v_pos = __ldcg(vcache + static_cast<size_t>(pos) * hs + tid);
+
+  // RoPE on q (this head) and on the new key row, rope_kernel.cu as compiled (elementwise.cu)
   if (tid < hs / 2) {
     const float* qg = P.q + static_cast<size_t>(head) * hs;
-    const float* kg = P.k_raw + head_offset;
-    int i0, i1, ci;
+    const float* kg = P.k_raw + kvh * hs;
+    int i0, i1;
     if (P.flavour == KLLM_FLAVOUR_LLAMA2) {
-      i0 = 2 * tid, i1 = 2 * tid + 1, ci = 2 * tid;  // head_dim = idx % head_size
+      i0 = 2 * tid, i1 = 2 * tid + 1;
     } else {
-      i0 = tid, i1 = tid + hs / 2, ci = 2 * tid;      // sin[pos*hs + head_dim*2]
+      i0 = tid, i1 = tid + hs / 2;
     }
+    const int ci = 2 * tid;
     const float fci = P.sin_cache[static_cast<size_t>(pos) * hs + ci];
     const float fcr = P.cos_cache[static_cast<size_t>(pos) * hs + ci];
     const float q0 = __ldcg(qg + i0), q1 = __ldcg(qg + i1);
@@ -259,35 +315,56 @@ __device__ void attention_phase(const Params& P, const Phase& ph, int head, int 
     const float r1 = __fmaf_rn(fci, k0, __fmul_rn(fcr, k1));
     k_s[i0] = r0;
     k_s[i1] = r1;
-    if (head % P.kv_mul == 0) {  // one writer per kv head puts the rotated key into the cache
-      kcache[static_cast<size_t>(pos) * kv_dim + i0] = r0;
-      kcache[static_cast<size_t>(pos) * kv_dim + i1] = r1;
+    if (head % P.kv_mul == 0) {  // one writer per kv head stores the rotated key
+      kcache[(static_cast<size_t>(i0 >> 2) * seq_len + pos) * 4 + (i0 & 3)] = r0;
+      kcache[(static_cast<size_t>(i1 >> 2) * seq_len + pos) * 4 + (i1 & 3)] = r1;
     }
   }
   consumer_sync();
 
+  // ---- scores: one left-to-right FFMA chain per timestep (mha_kernel.cu:61-91) ---------------
   const float scale = 1.f / sqrtf(static_cast<float>(hs));
   const float4* q4 = reinterpret_cast<const float4*>(q_s);
-  for (int t = tid; t <= pos; t += kConsumerThreads) {
-    const float4* k4 = (t == pos) ? reinterpret_cast<const float4*>(k_s)
-                                  : reinterpret_cast<const float4*>(kcache + static_cast<size_t>(t) * kv_dim);
-    float score = 0.0f;
+  const int n_tiles = attn_tiles(pos, T);
+  for (int j = 0; j < n_tiles; ++j) {
+    const int t0 = j * T;
+    const int nt = min(T, pos - t0);
+    mbar_wait(&full_bar[pipe.slot], pipe.parity);
+    const float4* tile = reinterpret_cast<const float4*>(stages + static_cast<size_t>(pipe.slot) * P.stage_bytes);
+    if (tid < nt) {
+      float score = 0.0f;
 #pragma unroll 4
-    for (int i = 0; i < (hs >> 2); ++i) {
-      const float4 kv = k4[i];
-      const float4 qv = q4[i];
+      for (int c = 0; c < (hs >> 2); ++c) {
+        const float4 kv = tile[c * T + tid];
+        const float4 qv = q4[c];
+        score = __fmaf_rn(kv.x, qv.x, score);
+        score = __fmaf_rn(kv.y, qv.y, score);
+        score = __fmaf_rn(kv.z, qv.z, score);
+        score = __fmaf_rn(kv.w, qv.w, score);
+      }
+      score_head[t0 + tid] = __fmul_rn(score, scale);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
+    pipe.advance(S);
+  }
+  if (tid == 0) {  // t == pos from the freshly rotated key
+    const float4* k4 = reinterpret_cast<const float4*>(k_s);
+    float score = 0.0f;
+    for (int c = 0; c < (hs >> 2); ++c) {
+      const float4 kv = k4[c];
+      const float4 qv = q4[c];
       score = __fmaf_rn(kv.x, qv.x, score);
       score = __fmaf_rn(kv.y, qv.y, score);
       score = __fmaf_rn(kv.z, qv.z, score);
       score = __fmaf_rn(kv.w, qv.w, score);
     }
-    score_head[t] = __fmul_rn(score, scale);
+    score_head[pos] = __fmul_rn(score, scale);
   }
   consumer_sync();
 
-  // softmax, mha_kernel.cu:7-45 (256 strided lanes + cub block reduce order)
+  // ---- softmax, mha_kernel.cu:7-45 (256 strided lanes + cub block-reduce order) -----------------
   const int size = pos + 1;
-  const int lane = tid & 31, warp = tid >> 5;
   float max_val = tid < size ? score_head[tid] : -FLT_MAX;
   for (int i = tid + kConsumerThreads; i < size; i += kConsumerThreads)
     max_val = fmaxf(max_val, score_head[i]);
@@ -320,34 +397,26 @@ __device__ void attention_phase(const Params& P, const Phase& ph, int head, int 
   for (int i = tid; i < size; i += kConsumerThreads) score_head[i] = score_head[i] / sum;
   consumer_sync();
 
-  // weighted value sum, mha_kernel.cu:97-109: one FFMA chain per output element
-  const int vec_per_row = hs >> 2;
-  const int n_tiles = (size + kVTile - 1) / kVTile;
-  auto stage = [&](int tile, int buf) {
-    const int t0 = tile * kVTile;
-    float4* dst = reinterpret_cast<float4*>(v_s + static_cast<size_t>(buf) * kVTile * hs);
-    for (int e = tid; e < kVTile * vec_per_row; e += kConsumerThreads) {
-      const int tt = e / vec_per_row, c = e % vec_per_row;
-      if (t0 + tt <= pos)
-        dst[e] = *reinterpret_cast<const float4*>(vcache + static_cast<size_t>(t0 + tt) * kv_dim + 4 * c);
-    }
-  };
+  // ---- weighted value sum, mha_kernel.cu:97-109: one FFMA chain per output element ----------------
   float value = 0.0f;
-  stage(0, 0);
-  consumer_sync();
-  for (int tile = 0; tile < n_tiles; ++tile) {
-    const int buf = tile & 1;
-    if (tile + 1 < n_tiles) stage(tile + 1, buf ^ 1);
+  for (int j = 0; j < n_tiles; ++j) {
+    const int t0 = j * T;
+    const int nt = min(T, pos - t0);
+    mbar_wait(&full_bar[pipe.slot], pipe.parity);
     if (tid < hs) {
-      const float* vt = v_s + static_cast<size_t>(buf) * kVTile * hs + tid;
-      const int t0 = tile * kVTile;
-      const int cnt = min(kVTile, size - t0);
+      const float* vt = reinterpret_cast<const float*>(stages + static_cast<size_t>(pipe.slot) * P.stage_bytes) + tid;
+      const float* pr = score_head + t0;
 #pragma unroll 8
-      for (int tt = 0; tt < cnt; ++tt) value = __fmaf_rn(score_head[t0 + tt], vt[tt * hs], value);
+      for (int tt = 0; tt < nt; ++tt) value = __fmaf_rn(pr[tt], vt[tt * hs], value);
     }
-    consumer_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
+    pipe.advance(S);
   }
-  if (tid < hs) P.attn_out[static_cast<size_t>(head) * hs + tid] = value;
+  if (tid < hs) {
+    value = __fmaf_rn(score_head[pos], v_pos, value);
+    P.attn_out[static_cast<size_t>(head) * hs + tid] = value;
+  }
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------
@@ -359,6 +428,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
   __shared__ float s_bcast;
   __shared__ float s_argv[kConsumerWarps];
   __shared__ int s_argi[kConsumerWarps];
+  // The ring leaves only a few KB of L1, so everything the inner loops touch lives in shared
+  // memory or registers: the consumer's and the producer's current schedule entries are copied
+  // here (they are usually in different phases).
+  __shared__ Phase s_phase_cons;
+  __shared__ Phase s_phase_prod;
 
   float* xs = reinterpret_cast<float*>(smem);
   unsigned char* stages = smem + P.xbuf_bytes;
@@ -384,11 +458,64 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
 
   // =============================== producer warp ===============================================
   if (is_producer) {
-    const uint64_t policy = policy_evict_first();
-    for (int tok = 0; tok < P.n_tokens; ++tok) {
+    const uint64_t policy = policy_evict_first();  // weights: streamed once per token
+    const uint64_t policy_kv = policy_evict_last();  // KV tiles: re-read every token, keep in L2
+    int ppos = P.state->pos;
+    for (int tok = 0; tok < P.n_tokens; ++tok, ++ppos) {
       for (int pi = 0; pi < P.n_phases; ++pi) {
-        const Phase& ph = P.phases[pi];
-        if (ph.kind != kPhaseGemv) continue;
+        {
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(P.phases + pi);
+          uint32_t* dst = reinterpret_cast<uint32_t*>(&s_phase_prod);
+          __syncwarp();
+          for (int i = lane; i < static_cast<int>(sizeof(Phase) / 4); i += 32) dst[i] = __ldg(src + i);
+          __syncwarp();
+        }
+        const Phase& ph = s_phase_prod;
+        unsigned long long* pstamp = (P.prof != nullptr && tok == P.prof_token && lane == 0)
+                                         ? P.prof + (static_cast<size_t>(cta) * P.n_phases + pi) * 8
+                                         : nullptr;
+        (void)pstamp;
+        if (ph.kind == kPhaseAttention) {
+          if (cta >= P.head_num || ppos == 0) continue;
+          // rows t < pos of this head: final since the previous token.  Order the async-proxy
+          // reads after the grid barrier that closed the previous token's attention phase.
+          if (tok > 0 && lane == 0) {
+            const unsigned need = P.barrier_base +
+                                  static_cast<unsigned>((tok - 1) * P.n_phases + pi + 1) * static_cast<unsigned>(G);
+            while (static_cast<int>(ld_acquire_u32(P.barrier) - need) < 0) {
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
+          __syncwarp();
+          const int hs = P.head_size, T = P.attn_tile;
+          const int kvh = cta / P.kv_mul;
+          const size_t head_block =
+              (static_cast<size_t>(ph.layer) * (P.kv_dim / hs) + kvh) * P.seq_len * hs;
+          const float* kbase = P.key_cache + head_block;
+          const float* vbase = P.value_cache + head_block;
+          const int n_tiles = attn_tiles(ppos, T);
+          for (int kv = 0; kv < 2; ++kv) {
+            for (int j = 0; j < n_tiles; ++j) {
+              const int t0 = j * T;
+              const int nt = min(T, ppos - t0);
+              mbar_wait(&empty_bar[pipe.slot], pipe.parity ^ 1u);
+              unsigned char* dst = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
+              if (lane == 0) mbar_expect_tx(&full_bar[pipe.slot], static_cast<uint32_t>(nt) * hs * 4);
+              __syncwarp();
+              if (kv == 0) {
+                if (lane < (hs >> 2))
+                  bulk_g2s(dst + static_cast<size_t>(lane) * T * 16,
+                           kbase + (static_cast<size_t>(lane) * P.seq_len + t0) * 4,
+                           static_cast<uint32_t>(nt) * 16, &full_bar[pipe.slot], policy_kv);
+              } else if (lane == 0) {
+                bulk_g2s(dst, vbase + static_cast<size_t>(t0) * hs, static_cast<uint32_t>(nt) * hs * 4,
+                         &full_bar[pipe.slot], policy_kv);
+              }
+              pipe.advance(S);
+            }
+          }
+          continue;
+        }
         const int u0 = static_cast<int>(static_cast<long long>(cta) * ph.units / G);
         const int u1 = static_cast<int>(static_cast<long long>(cta + 1) * ph.units / G);
         const int rpu = ph.swiglu ? 2 : 1;
@@ -439,6 +566,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
             }
           }
         }
+        
       }
     }
     return;
@@ -457,13 +585,21 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
 
     const bool prof_on = P.prof != nullptr && tok == P.prof_token && tid == 0;
     for (int pi = 0; pi < P.n_phases; ++pi) {
-      const Phase& ph = P.phases[pi];
+      {
+        // (the grid barrier that ended the previous phase is the hazard fence for this copy)
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.phases + pi);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_phase_cons);
+        if (tid < static_cast<int>(sizeof(Phase) / 4)) dst[tid] = __ldg(src + tid);
+        consumer_sync();
+      }
+      const Phase& ph = s_phase_cons;
       unsigned long long* stamp =
-          prof_on ? P.prof + (static_cast<size_t>(cta) * P.n_phases + pi) * 4 : nullptr;
+          prof_on ? P.prof + (static_cast<size_t>(cta) * P.n_phases + pi) * 8 : nullptr;
       if (stamp) stamp[0] = global_ns();
 
       if (ph.kind == kPhaseAttention) {
-        if (cta < P.head_num) attention_phase(P, ph, cta, pos, xs, s_warp, &s_bcast);
+        if (cta < P.head_num)
+          attention_phase(P, ph, cta, pos, xs, s_warp, &s_bcast, stages, full_bar, empty_bar, pipe);
         if (stamp) stamp[1] = stamp[2] = global_ns();
         grid_barrier(P.barrier, bar_target, G);
         if (stamp) stamp[3] = global_ns();
@@ -476,7 +612,20 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
         const float* xg = ph.x_from_emb ? emb_row : ph.x;
         const float4* xg4 = reinterpret_cast<const float4*>(xg);
         float4* xs4w = reinterpret_cast<float4*>(xs);
-        for (int i = tid; i < (M >> 2); i += kConsumerThreads) xs4w[i] = __ldcg(xg4 + i);
+        const int n4 = M >> 2;
+        // up to kMaxNormRegs float4 of the (static) norm weight ride in registers while x arrives
+        constexpr int kMaxNormRegs = 4;
+        float4 nw[kMaxNormRegs];
+        const float4* nw4 = reinterpret_cast<const float4*>(ph.norm_w);
+        const bool norm_regs = ph.norm_w != nullptr && n4 <= kMaxNormRegs * kConsumerThreads;
+        if (norm_regs) {
+#pragma unroll
+          for (int k = 0; k < kMaxNormRegs; ++k) {
+            const int i = tid + k * kConsumerThreads;
+            if (i < n4) nw[k] = __ldg(nw4 + i);
+          }
+        }
+        for (int i = tid; i < n4; i += kConsumerThreads) xs4w[i] = __ldcg(xg4 + i);
         consumer_sync();
         if (ph.norm_w != nullptr) {
           if (warp == 0) {
@@ -485,8 +634,24 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
           }
           consumer_sync();
           const float sc = s_bcast;
-          for (int i = tid; i < M; i += kConsumerThreads)
-            xs[i] = __fmul_rn(__fmul_rn(sc, xs[i]), ph.norm_w[i]);  // rmsnorm_kernel.cu:41-45
+          // rmsnorm_kernel.cu:41-45: (scale * x) * w
+          if (norm_regs) {
+#pragma unroll
+            for (int k = 0; k < kMaxNormRegs; ++k) {
+              const int i = tid + k * kConsumerThreads;
+              if (i < n4) {
+                float4 v = xs4w[i];
+                v.x = __fmul_rn(__fmul_rn(sc, v.x), nw[k].x);
+                v.y = __fmul_rn(__fmul_rn(sc, v.y), nw[k].y);
+                v.z = __fmul_rn(__fmul_rn(sc, v.z), nw[k].z);
+                v.w = __fmul_rn(__fmul_rn(sc, v.w), nw[k].w);
+                xs4w[i] = v;
+              }
+            }
+          } else {
+            for (int i = tid; i < M; i += kConsumerThreads)
+              xs[i] = __fmul_rn(__fmul_rn(sc, xs[i]), ph.norm_w[i]);
+          }
           consumer_sync();
         }
       }
@@ -499,78 +664,109 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
       const int row_bytes = M * wbytes;
       const float* residual = ph.residual_from_emb ? emb_row : ph.residual;
 
-      auto epilogue = [&](int unit, float d0, float d1) {
+      // bias / residual of a unit are fetched BEFORE its dot product so their L2 latency hides
+      // behind the accumulation (lane 0 only)
+      auto prefetch_addend = [&](int unit, float& bias_v, float& res_v) {
+        bias_v = 0.f, res_v = 0.f;
+        if (ph.swiglu || lane != 0) return;
+        const RowRef rr = resolve_row(ph, unit, 0);
+        if (ph.seg[rr.seg].bias != nullptr) bias_v = __ldg(ph.seg[rr.seg].bias + rr.row);
+        if (residual != nullptr) res_v = __ldcg(residual + rr.row);
+      };
+      auto epilogue = [&](int unit, float d0, float d1, float bias_v, float res_v) {
         // lane 0 only
         if (ph.swiglu) {
           ph.seg[0].out[unit] = swiglu_ref(d0, d1);
           return;
         }
         const RowRef rr = resolve_row(ph, unit, 0);
+        const Seg& sg = ph.seg[rr.seg];
         float v = d0;
-        if (ph.seg[rr.seg].bias != nullptr) v = __fadd_rn(v, ph.seg[rr.seg].bias[rr.row]);
-        if (residual != nullptr) v = __fadd_rn(__ldcg(residual + rr.row), v);
-        ph.seg[rr.seg].out[static_cast<long long>(pos) * ph.seg[rr.seg].pos_stride + rr.row] = v;
+        if (sg.bias != nullptr) v = __fadd_rn(v, bias_v);       // matmul.cpp:74-77: out + bias
+        if (residual != nullptr) v = __fadd_rn(res_v, v);       // llama3.cpp:683,719: x + out
+        if (sg.head_major) {
+          const int hs = P.head_size;
+          sg.out[(static_cast<size_t>(rr.row / hs) * P.seq_len + pos) * hs + rr.row % hs] = v;
+        } else {
+          sg.out[static_cast<long long>(pos) * sg.pos_stride + rr.row] = v;
+        }
         if (ph.argmax) arg_fold(best, v, rr.row);
       };
 
+      long long cyc_wait = 0, cyc_rows = 0;
+      long long cyc4[4] = {0, 0, 0, 0};
       if (ph.chunks_per_row == 1) {
         const int ups = ph.rows_per_stage / rpu;
         for (int u = u0; u < u1; u += ups) {
           const int n = min(ups, u1 - u);
+          const long long c0 = stamp ? clock64() : 0;
           mbar_wait(&full_bar[pipe.slot], pipe.parity);
+          const long long c1 = stamp ? clock64() : 0;
+          cyc_wait += c1 - c0;
           const unsigned char* sbase = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
           // units go round-robin over ALL consumer warps across stages (a stage may hold fewer
           // units than there are warps)
           const int first = ((warp - (u - u0)) % kConsumerWarps + kConsumerWarps) % kConsumerWarps;
           for (int i = first; i < n; i += kConsumerWarps) {
             const int unit = u + i;
+            float bias_v, res_v;
+            const long long t_a = stamp ? clock64() : 0;
+            prefetch_addend(unit, bias_v, res_v);
+            const long long t_b = stamp ? clock64() : 0;
             if (P.group_size == 0) {
               if (ph.swiglu) {
                 const float4* w[2] = {reinterpret_cast<const float4*>(sbase + static_cast<size_t>(2 * i) * row_bytes),
                                       reinterpret_cast<const float4*>(sbase + static_cast<size_t>(2 * i + 1) * row_bytes)};
                 float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
                 accum_f32<2>(w, xs4, M >> 2, lane, acc);
+                const long long t_c = stamp ? clock64() : 0;
                 const float d0 = block128_sum_vt(acc[0]);
                 const float d1 = block128_sum_vt(acc[1]);
-                if (lane == 0) epilogue(unit, d0, d1);
+                const long long t_d = stamp ? clock64() : 0;
+                if (lane == 0) epilogue(unit, d0, d1, bias_v, res_v);
+                if (stamp) {
+                  cyc4[0] += t_b - t_a, cyc4[1] += t_c - t_b, cyc4[2] += t_d - t_c, cyc4[3] += clock64() - t_d;
+                }
               } else {
                 const float4* w[1] = {reinterpret_cast<const float4*>(sbase + static_cast<size_t>(i) * row_bytes)};
                 float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
                 accum_f32<1>(w, xs4, M >> 2, lane, acc);
+                const long long t_c = stamp ? clock64() : 0;
                 const float d0 = block128_sum_vt(acc[0]);
-                if (lane == 0) epilogue(unit, d0, 0.f);
+                const long long t_d = stamp ? clock64() : 0;
+                if (lane == 0) epilogue(unit, d0, 0.f, bias_v, res_v);
+                if (stamp) {
+                  cyc4[0] += t_b - t_a, cyc4[1] += t_c - t_b, cyc4[2] += t_d - t_c, cyc4[3] += clock64() - t_d;
+                }
               }
             } else {
               if (ph.swiglu) {
                 const uint32_t* w[2];
                 const float* sc[2];
-                long long eb[2];
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
                   w[r] = reinterpret_cast<const uint32_t*>(sbase + static_cast<size_t>(2 * i + r) * row_bytes);
                   sc[r] = reinterpret_cast<const float*>(sbase + ph.scale_off +
                                                          static_cast<size_t>(2 * i + r) * ph.scale_row_bytes);
-                  eb[r] = static_cast<long long>(unit) * M;
                 }
                 float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                accum_w8<2>(w, sc, eb, xs4, M, ph.group_shift, ph.group_size, lane, acc);
+                accum_w8<2>(w, sc, xs4, M, ph.group_shift, ph.group_size, lane, acc);
                 const float d0 = block128_sum_quad(acc[0]);
                 const float d1 = block128_sum_quad(acc[1]);
-                if (lane == 0) epilogue(unit, d0, d1);
+                if (lane == 0) epilogue(unit, d0, d1, bias_v, res_v);
               } else {
-                const RowRef rr = resolve_row(ph, unit, 0);
                 const uint32_t* w[1] = {reinterpret_cast<const uint32_t*>(sbase + static_cast<size_t>(i) * row_bytes)};
                 const float* sc[1] = {reinterpret_cast<const float*>(sbase + ph.scale_off +
                                                                      static_cast<size_t>(i) * ph.scale_row_bytes)};
-                const long long eb[1] = {static_cast<long long>(rr.row) * M};
                 float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
-                accum_w8<1>(w, sc, eb, xs4, M, ph.group_shift, ph.group_size, lane, acc);
+                accum_w8<1>(w, sc, xs4, M, ph.group_shift, ph.group_size, lane, acc);
                 const float d0 = block128_sum_quad(acc[0]);
-                if (lane == 0) epilogue(unit, d0, 0.f);
+                if (lane == 0) epilogue(unit, d0, 0.f, bias_v, res_v);
               }
             }
           }
           __syncwarp();
+          if (stamp) cyc_rows += clock64() - c1;
           if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
           pipe.advance(S);
         }
@@ -580,6 +776,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
         // thread still sees its packs in increasing order.
         for (int u = u0; u < u1; ++u) {
           const bool mine = ((u - u0) % kConsumerWarps) == warp;
+          float bias_v = 0.f, res_v = 0.f;
+          if (mine) prefetch_addend(u, bias_v, res_v);
           float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
           for (int c = 0; c < ph.chunks_per_row; ++c) {
             const int e0 = c * ph.chunk_elems;
@@ -596,7 +794,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
           }
           if (mine) {
             const float d0 = block128_sum_vt(acc[0]);
-            if (lane == 0) epilogue(u, d0, 0.f);
+            if (lane == 0) epilogue(u, d0, 0.f, bias_v, res_v);
           }
         }
       }
@@ -617,7 +815,14 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
           P.arg_idx[cta] = b.i;
         }
       }
-      if (stamp) stamp[2] = global_ns();
+      if (stamp) {
+        stamp[2] = global_ns();
+        stamp[4] = static_cast<unsigned long long>(cyc4[0]);
+        stamp[5] = static_cast<unsigned long long>(cyc4[1]);
+        stamp[6] = static_cast<unsigned long long>(cyc4[2]);
+        stamp[7] = static_cast<unsigned long long>(cyc4[3]);
+        (void)cyc_wait, (void)cyc_rows;
+      }
       grid_barrier(P.barrier, bar_target, G);
       if (stamp) stamp[3] = global_ns();
     }
@@ -671,7 +876,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   // shapes the ring handles: 16-byte rows, 128-byte aligned kv rows (L1-cached reads stay exact)
   if ((dim & 3) || (hid & 3) || (q_rows & 3) || (hs & 3) || hs > mega::kConsumerThreads) return KLLM_E_UNSUPPORTED;
   if (int8 && ((dim & 15) || (hid & 15) || (q_rows & 15) || (m.group_size & 3))) return KLLM_E_UNSUPPORTED;
-  if ((kvd * 4) % 128 != 0) return KLLM_E_UNSUPPORTED;
+  if ((hs * 4) % 16 != 0) return KLLM_E_UNSUPPORTED;
   if (int8) {
     const int dims[3] = {dim, hid, q_rows};
     for (int d : dims)
@@ -681,7 +886,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   // ---- shared memory plan -----------------------------------------------------------------------
   const int max_in = std::max(std::max(dim, hid), q_rows);
   int xbuf = max_in * 4;
-  const int attn_ws = (2 * hs + 2 * mega::kVTile * hs) * 4;
+  const int attn_ws = 2 * hs * 4;
   xbuf = std::max(xbuf, attn_ws);
   xbuf = (xbuf + 127) & ~127;
   const int budget = max_smem - xbuf - 2048;  // static smem + slack
@@ -696,6 +901,8 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   if (stages < 2) return KLLM_E_UNSUPPORTED;
   stage_bytes_ = stage_bytes;
   stages_ = stages;
+  attn_tile_ = std::min(stage_bytes / (hs * 4), mega::kConsumerThreads) & ~31;
+  if (attn_tile_ < 32) return KLLM_E_UNSUPPORTED;
   xbuf_bytes_ = xbuf;
   smem_bytes_ = static_cast<size_t>(xbuf) + static_cast<size_t>(stages) * stage_bytes;
 
@@ -754,10 +961,10 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       p.x_from_emb = (l == 0);
       p.norm_w = m.attn_norm[l];
       p.norm_eps = eps;
-      p.seg[0] = {m.wq[l], int8 ? m.sq[l] : nullptr, m.bq ? m.bq[l] : nullptr, m.q, 0, q_rows};
-      p.seg[1] = {m.wk[l], int8 ? m.sk[l] : nullptr, m.bk ? m.bk[l] : nullptr, m.k_raw, 0, kvd};
+      p.seg[0] = {m.wq[l], int8 ? m.sq[l] : nullptr, m.bq ? m.bq[l] : nullptr, m.q, 0, q_rows, 0};
+      p.seg[1] = {m.wk[l], int8 ? m.sk[l] : nullptr, m.bk ? m.bk[l] : nullptr, m.k_raw, 0, kvd, 0};
       p.seg[2] = {m.wv[l], int8 ? m.sv[l] : nullptr, m.bv ? m.bv[l] : nullptr,
-                  m.value_cache + layer_off, kvd, kvd};
+                  m.value_cache + layer_off, 0, kvd, 1};
       p.units = q_rows + 2 * kvd;
       if (int rc = plan(p)) return rc;
       ph.push_back(p);
@@ -774,7 +981,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       p.in_dim = q_rows;
       p.n_seg = 1;
       p.x = m.attn_out;
-      p.seg[0] = {m.wo[l], int8 ? m.so[l] : nullptr, nullptr, m.x, 0, dim};
+      p.seg[0] = {m.wo[l], int8 ? m.so[l] : nullptr, nullptr, m.x, 0, dim, 0};
       p.residual = m.x;
       p.residual_from_emb = (l == 0);
       p.units = dim;
@@ -790,8 +997,8 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       p.x = m.x;
       p.norm_w = m.ffn_norm[l];
       p.norm_eps = eps;
-      p.seg[0] = {m.w1[l], int8 ? m.s1[l] : nullptr, nullptr, m.h, 0, hid};
-      p.seg[1] = {m.w3[l], int8 ? m.s3[l] : nullptr, nullptr, nullptr, 0, hid};
+      p.seg[0] = {m.w1[l], int8 ? m.s1[l] : nullptr, nullptr, m.h, 0, hid, 0};
+      p.seg[1] = {m.w3[l], int8 ? m.s3[l] : nullptr, nullptr, nullptr, 0, hid, 0};
       p.units = hid;
       if (int rc = plan(p)) return rc;
       ph.push_back(p);
@@ -802,7 +1009,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       p.in_dim = hid;
       p.n_seg = 1;
       p.x = m.h;
-      p.seg[0] = {m.w2[l], int8 ? m.s2[l] : nullptr, nullptr, m.x, 0, dim};
+      p.seg[0] = {m.w2[l], int8 ? m.s2[l] : nullptr, nullptr, m.x, 0, dim, 0};
       p.residual = m.x;
       p.units = dim;
       if (int rc = plan(p)) return rc;
@@ -817,7 +1024,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
     p.x = m.x;
     p.norm_w = m.final_norm;
     p.norm_eps = eps;
-    p.seg[0] = {m.wcls, int8 ? m.scls : nullptr, nullptr, m.logits, 0, m.vocab_size};
+    p.seg[0] = {m.wcls, int8 ? m.scls : nullptr, nullptr, m.logits, 0, m.vocab_size, 0};
     p.units = m.vocab_size;
     p.argmax = 1;
     if (int rc = plan(p)) return rc;
@@ -872,6 +1079,7 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
   P.num_stages = stages_;
   P.stage_bytes = stage_bytes_;
   P.xbuf_bytes = xbuf_bytes_;
+  P.attn_tile = attn_tile_;
   P.group_size = m.group_size;
   P.dim = m.dim;
   P.vocab_size = m.vocab_size;

@@ -225,15 +225,11 @@ class Decoder:
         return buf
 
     def kv_cache(self):
-        """(key, value) caches as torch views [L, seq_len, kv_dim] (no copy)."""
-        import torch
+        """(key, value) caches as numpy arrays [L, seq_len, kv_dim] in the reference layout."""
+        import numpy as np
         s = self.shape
-        n = s.layer_num * s.seq_len * s.kv_dim
-
-        def view(ptr):
-            iface = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 3}
-            holder = type("_CudaView", (), {"__cuda_array_interface__": iface})()
-            return torch.as_tensor(holder, device="cuda").view(s.layer_num, s.seq_len, s.kv_dim)
-
-        return (view(self.lib.kllm_decoder_key_cache(self.handle)),
-                view(self.lib.kllm_decoder_value_cache(self.handle)))
+        k = np.empty((s.layer_num, s.seq_len, s.kv_dim), np.float32)
+        v = np.empty_like(k)
+        check(self.lib.kllm_decoder_read_kv(self.handle, k.ctypes.data_as(ctypes.c_void_p),
+                                            v.ctypes.data_as(ctypes.c_void_p)), "kllm_decoder_read_kv")
+        return k, v

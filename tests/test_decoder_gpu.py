@@ -86,8 +86,8 @@ def test_golden_logits(kllm_lib, oracle, name, quant, flavour, bias):
         assert nxt == int(np.argmax(g["logits"][t])) == o_next
     k, v = dec.kv_cache(); ok, ov = om.kv_cache()
     n = len(g["tokens"])
-    assert np.abs(k[:, :n].cpu().numpy() - ok[:, :n]).max() < TOL
-    assert np.abs(v[:, :n].cpu().numpy() - ov[:, :n]).max() < TOL
+    assert np.abs(k[:, :n] - ok[:, :n]).max() < TOL
+    assert np.abs(v[:, :n] - ov[:, :n]).max() < TOL
     om.close(); dec.close()
 
 

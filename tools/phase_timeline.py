@@ -23,14 +23,14 @@ def main():
     dec = Decoder(shape, synth_weights(shape, "cuda", 1235))
     assert dec.engine == "persistent"
     dec.generate(1, 0, 8)
-    cap = 200 * 2000 * 4
+    cap = 200 * 2000 * 8
     buf = np.zeros(cap, np.uint64)
     g, p = ctypes.c_int32(), ctypes.c_int32()
     n = a.pos + 1
     check(dec.lib.kllm_decoder_profile(dec.handle, 1, 0, n, a.pos, buf.ctypes.data_as(ctypes.c_void_p), cap,
                                        ctypes.byref(g), ctypes.byref(p)), "profile")
     G, P = g.value, p.value
-    st = buf[: G * P * 4].reshape(G, P, 4).astype(np.int64)
+    st = buf[: G * P * 8].reshape(G, P, 8).astype(np.int64)
     t0 = st[:, 0, 0].min()
     st = (st - t0) / 1e3  # us
     L = shape.layer_num
@@ -49,6 +49,18 @@ def main():
     idx = [P - 1]
     print(f"{'cls':>10} {1:5d} {dur[idx].mean():9.2f} {np.median(stage[:, idx]):8.2f} {np.median(work[:, idx]):9.2f} "
           f"{work[:, idx].max(axis=0).mean():9.2f} {bar[:, idx].min(axis=0).mean():11.2f} {np.median(bar[:, idx]):11.2f}")
+    # how far ahead of the consumers the producer finishes issuing each phase's copies
+    lead = st[:, :, 0] * 0
+    gem = [i for i in range(P) if i % 5 != 1 or i == P - 1]
+    print(f"# producer lead (consumer enters phase - producer finished issuing it), us: "
+          + " ".join(f"{nm}={np.median(lead[40:, [l * 5 + k for l in range(1, L)]]):.2f}" for k, nm in enumerate(names) if k != 1))
+    raw = buf[: G * P * 8].reshape(G, P, 8).astype(np.float64)
+    print("# warp 0, cycles summed over its units in the phase: prefetch / accumulate / reduce / epilogue")
+    for k, nm in enumerate(names):
+        if k == 1:
+            continue
+        idx = [l * 5 + k for l in range(L)]
+        print(f"#   {nm:>5}: " + " / ".join(f"{np.median(raw[:, idx, 4 + q]):8.0f}" for q in range(4)))
     print(f"# sum of phase durations: {dur.sum():.1f} us; barrier_min = time the LAST arriving CTA spends in the barrier")
 
 
