@@ -69,7 +69,8 @@ SHAPES = {
     "tiny-shared": ModelShape("tiny-shared-fp32", 64, 172, 2, 4, 4, 512, 64, True),
     "tiny-int8": ModelShape("tiny-int8", 128, 384, 2, 4, 2, 512, 64, group_size=64),
     "tiny-qwen": ModelShape("tiny-qwen2", 128, 344, 2, 4, 2, 640, 96, True, flavour="qwen2"),
-    "small": ModelShape("small-fp32", 288, 768, 3, 6, 6, 4096, 160),
+    "small": ModelShape("small-fp32", 288, 768, 3, 9, 3, 4096, 160),
+    "small-hs48": ModelShape("small-hs48-fp32", 288, 768, 3, 6, 6, 4096, 160),
     "small-int8": ModelShape("small-int8", 256, 768, 2, 4, 2, 1024, 96, group_size=64),
     "small-qwen": ModelShape("small-qwen2", 256, 704, 2, 4, 2, 1536, 128, True, flavour="qwen2"),
 }

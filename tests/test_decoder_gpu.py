@@ -115,8 +115,8 @@ def _synth_file(tmp_path, key, seed):
     return shape, w, path
 
 
-@pytest.mark.parametrize("key,steps", [("tiny", 64), ("tiny-shared", 64), ("small", 160), ("tiny-int8", 64),
-                                       ("small-int8", 96)])
+@pytest.mark.parametrize("key,steps", [("tiny", 64), ("tiny-shared", 64), ("small", 160), ("small-hs48", 160),
+                                       ("tiny-int8", 64), ("small-int8", 96)])
 def test_free_running_decode_identical_to_reference_cuda(kllm_lib, ref, tmp_path, key, steps):
     """Greedy decode feeding its own output: token ids AND final logits identical to the
     reference's CUDA path (demo/main.cpp loop), every position up to seq_len."""
@@ -226,3 +226,35 @@ def test_default_engine_selection(kllm_lib, monkeypatch):
     dec = Decoder(shape, to_device(w))  # 4-byte scale rows: not bulk-copyable
     assert dec.engine == "graph"
     dec.close()
+
+
+RING_STRESS = {
+    # many ring stages per phase / several ring revolutions per phase / MHA with 32 kv heads:
+    # dim, hidden, layers, heads, kv_heads, vocab, seq_len   (regressions: mbarrier phase aliasing)
+    "dim2048_hid5632": (2048, 5632, 1, 32, 4, 1024, 64),
+    "dim2048_vocab32000": (2048, 2048, 1, 32, 4, 32000, 64),
+    "dim2048_mha32": (2048, 2048, 1, 32, 32, 1024, 64),
+    "dim1024_hid5632": (1024, 5632, 2, 16, 4, 1024, 64),
+}
+
+
+@pytest.mark.parametrize("name", sorted(RING_STRESS))
+def test_persistent_equals_graph_on_ring_stress_shapes(kllm_lib, monkeypatch, name):
+    """The graph engine is checked bit for bit against the reference CUDA path above; here the
+    persistent megakernel must reproduce it (ids and logits) on shapes that drive the stage ring
+    through many revolutions per phase."""
+    from kuiperllama_b200 import Decoder, ModelShape, synth_weights
+    d, h, L, nh, nkv, V, S = RING_STRESS[name]
+    shape = ModelShape(name, d, h, L, nh, nkv, V, S)
+    w = synth_weights(shape, "cuda", 5)
+    monkeypatch.setenv("KLLM_ENGINE", "graph")
+    a = Decoder(shape, w)
+    ids_a = a.generate(1, 0, 48)
+    la = a.logits()
+    a.close()
+    monkeypatch.setenv("KLLM_ENGINE", "persistent")
+    b = Decoder(shape, w)
+    ids_b = b.generate(1, 0, 48)
+    assert ids_a == ids_b
+    assert_bit_equal(la, b.logits(), name)
+    b.close()

@@ -50,17 +50,16 @@ def main():
     print(f"{'cls':>10} {1:5d} {dur[idx].mean():9.2f} {np.median(stage[:, idx]):8.2f} {np.median(work[:, idx]):9.2f} "
           f"{work[:, idx].max(axis=0).mean():9.2f} {bar[:, idx].min(axis=0).mean():11.2f} {np.median(bar[:, idx]):11.2f}")
     # how far ahead of the consumers the producer finishes issuing each phase's copies
-    lead = st[:, :, 0] * 0
+    lead = st[:, :, 0] - st[:, :, 5]
     gem = [i for i in range(P) if i % 5 != 1 or i == P - 1]
     print(f"# producer lead (consumer enters phase - producer finished issuing it), us: "
           + " ".join(f"{nm}={np.median(lead[40:, [l * 5 + k for l in range(1, L)]]):.2f}" for k, nm in enumerate(names) if k != 1))
-    raw = buf[: G * P * 8].reshape(G, P, 8).astype(np.float64)
-    print("# warp 0, cycles summed over its units in the phase: prefetch / accumulate / reduce / epilogue")
-    for k, nm in enumerate(names):
-        if k == 1:
-            continue
-        idx = [l * 5 + k for l in range(L)]
-        print(f"#   {nm:>5}: " + " / ".join(f"{np.median(raw[:, idx, 4 + q]):8.0f}" for q in range(4)))
+    ai = [l * 5 + 1 for l in range(L)]
+    H = shape.head_num
+    sa = st[:H][:, ai, :]
+    print("# attention CTAs (us, median): rope %.2f | scores %.2f | softmax %.2f | values %.2f" % (
+        np.median(sa[:, :, 6] - sa[:, :, 0]), np.median(sa[:, :, 1] - sa[:, :, 6]),
+        np.median(sa[:, :, 7] - sa[:, :, 1]), np.median(sa[:, :, 2] - sa[:, :, 7])))
     print(f"# sum of phase durations: {dur.sum():.1f} us; barrier_min = time the LAST arriving CTA spends in the barrier")
 
 
