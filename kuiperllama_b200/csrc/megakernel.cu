@@ -39,188 +39,230 @@
 namespace kllm {
 namespace mega {
 
-// ---- attention phase: one CTA per query head (mha_kernel.cu:47-110 + rope_kernel.cu) ------------
-__device__ void attention_phase(const Params& P, const Phase& ph, int head, int pos, float* ws,
-                                float* s_warp, float* s_bcast, unsigned char* stages,
-                                uint64_t* full_bar, uint64_t* empty_bar, Ring& ring,
-                                unsigned long long* stamp) {
+// ---- attention phase (mha_kernel.cu:47-110 + rope_kernel.cu), two steps inside one schedule phase
+//
+// Per-SM TMA ingest is ~47 GB/s, so a head-per-CTA mapping (8 query heads of a GQA group each
+// re-reading the same 2 x pos x 256 B of KV on 32 SMs) is ingest-bound; instead the KV bytes are
+// read once and spread over every SM:
+//   step A (all CTAs): item (kv group g, K tile j) -> scores of ALL query heads of the group
+//       over the tile's timesteps (one FFMA chain per (head, t), reference order), written to the
+//       global [head][seq_len] score buffer; item (g, n_kt) = the current position: rotate the
+//       new key, store it, score it.  Each finished item bumps flags[g] (release).
+//   step B (few CTAs): item (g, value slab, head chunk): wait for flags[g] (acquire), one warp
+//       per head does the reference softmax (256 virtual lanes folded in cub order) into shared
+//       memory, then walks its FFMA chain over the slab's V tiles; all warps share the tiles.
+// No grid barrier between A and B: only the CTAs that own a B item wait, on their group's flag.
+struct AttnPlan {
+  int n_kt, n_vt, items_a, hpc, nchunks, items_b;
+};
+__device__ __forceinline__ AttnPlan attn_plan(const Params& P, int pos) {
+  AttnPlan a;
+  const AttnGeom g = attn_geom(P);
+  const int kv_heads = P.kv_dim / P.head_size;
+  a.n_kt = ceil_div(pos, g.tk);
+  a.n_vt = ceil_div(pos, g.tv);
+  a.items_a = kv_heads * (a.n_kt + 1);
+  const int cap = P.xbuf_bytes >> 2;
+  const int need = (pos + 1 + 3) & ~3;
+  int hpc = cap / need;  // heads whose probabilities fit the workspace
+  if (hpc > P.kv_mul) hpc = P.kv_mul;
+  if (hpc > kNW) hpc = kNW;
+  if (hpc < 1) hpc = 1;  // probabilities live in the global score buffer instead
+  a.hpc = hpc;
+  a.nchunks = ceil_div(P.kv_mul, hpc);
+  a.items_b = kv_heads * g.slabs * a.nchunks;
+  return a;
+}
+
+__device__ void attention_phase(const Params& P, const Phase& ph, int cta, int G, int pos, float* ws,
+                                unsigned char* stages, uint64_t* full_bar, uint64_t* empty_bar,
+                                Ring& ring, unsigned& flag_base, unsigned long long* stamp) {
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int hs = P.head_size, seq_len = P.seq_len, S = P.num_stages;
+  const int hs = P.head_size, seq_len = P.seq_len, S = P.num_stages, kv_mul = P.kv_mul;
   const AttnGeom g = attn_geom(P);
-  float* q_s = ws;       // [hs] rotated query
-  float* k_s = ws + hs;  // [hs] rotated key of the current position
-  const int kvh = head / P.kv_mul;
-  const size_t head_block = (static_cast<size_t>(ph.layer) * (P.kv_dim / hs) + kvh) * seq_len * hs;
-  float* kcache = P.key_cache + head_block;
-  const float* vcache = P.value_cache + head_block;
-  // scores / probabilities: shared memory when the context fits the workspace (the ring leaves
-  // almost no L1), else the global [head][seq_len] buffer the reference uses
-  const int smem_cap = (P.xbuf_bytes >> 2) - 2 * hs;
-  float* score = (pos + 1 <= smem_cap) ? (ws + 2 * hs) : (P.score + static_cast<size_t>(head) * seq_len);
-
-  // value of the current position for this lane's output dim (slab warps only)
-  float v_pos = 0.f;
-  if (warp < g.slabs && lane < g.sw)
-    v_pos = __ldcg(vcache + (static_cast<size_t>(warp) * seq_len + pos) * g.sw + lane);
-
-  // RoPE on q (this head) and on the new key row, rope_kernel.cu as compiled (elementwise.cu)
-  if (tid < hs / 2) {
-    const float* qg = P.q + static_cast<size_t>(head) * hs;
-    const float* kg = P.k_raw + kvh * hs;
-    int i0, i1;
-    if (P.flavour == KLLM_FLAVOUR_LLAMA2) {
-      i0 = 2 * tid, i1 = 2 * tid + 1;
-    } else {
-      i0 = tid, i1 = tid + hs / 2;
-    }
-    const int ci = 2 * tid;
-    const float fci = P.sin_cache[static_cast<size_t>(pos) * hs + ci];
-    const float fcr = P.cos_cache[static_cast<size_t>(pos) * hs + ci];
-    const float q0 = __ldcg(qg + i0), q1 = __ldcg(qg + i1);
-    q_s[i0] = __fmaf_rn(fcr, q0, -__fmul_rn(fci, q1));
-    q_s[i1] = __fmaf_rn(fci, q0, __fmul_rn(fcr, q1));
-    const float k0 = __ldcg(kg + i0), k1 = __ldcg(kg + i1);
-    const float r0 = __fmaf_rn(fcr, k0, -__fmul_rn(fci, k1));
-    const float r1 = __fmaf_rn(fci, k0, __fmul_rn(fcr, k1));
-    k_s[i0] = r0;
-    k_s[i1] = r1;
-    if (head % P.kv_mul == 0) {  // one writer per kv head stores the rotated key
-      kcache[(static_cast<size_t>(i0 >> 2) * seq_len + pos) * 4 + (i0 & 3)] = r0;
-      kcache[(static_cast<size_t>(i1 >> 2) * seq_len + pos) * 4 + (i1 & 3)] = r1;
-    }
-  }
-  consumer_sync();
-  if (stamp) stamp[6] = global_ns();
-
-  // ---- scores: one left-to-right FFMA chain per timestep (mha_kernel.cu:61-91).  A K tile is
-  // owned by one warp; each lane carries up to 8 timesteps (independent chains).
+  const AttnPlan pl = attn_plan(P, pos);
+  const int kv_heads = P.kv_dim / hs;
   const float scale = 1.f / sqrtf(static_cast<float>(hs));
-  const float4* q4 = reinterpret_cast<const float4*>(q_s);
-  const int n_kt = ceil_div(pos, g.tk);
-  const int km = g.tk >> 5;
-  for (int j = 0; j < n_kt; ++j) {
-    // Every warp observes every fill of every slot, in order (an mbarrier wait only tells parity:
-    // a warp that skipped a fill could mistake an older phase for the one it needs); only the
-    // owner touches the data and releases the slot.
-    mbar_wait(&full_bar[ring.slot], ring.parity);
-    if (ring.count % kNW == warp) {
+  float* q_s = ws;                 // [kv_mul][hs] rotated queries of one group
+  float* k_s = ws + kv_mul * hs;   // [hs] rotated key of the current position
+
+  // ================= step A: scores =================
+  for (int item = cta; item < pl.items_a; item += G) {
+    const int grp = item / (pl.n_kt + 1);
+    const int j = item % (pl.n_kt + 1);
+    const size_t head_block = (static_cast<size_t>(ph.layer) * kv_heads + grp) * seq_len * hs;
+    float* kcache = P.key_cache + head_block;
+    consumer_sync();  // previous item done with q_s / k_s
+    // RoPE of the group's queries (and, for the current-position item, of the new key row):
+    // rope_kernel.cu as compiled -- x' = fma(cos, x0, -(sin*x1)), y' = fma(sin, x0, cos*x1)
+    const int half = hs >> 1;
+    for (int idx = tid; idx < (kv_mul + 1) * half; idx += kConsumerThreads) {
+      const int hh = idx / half, pr = idx % half;
+      if (hh == kv_mul && j != pl.n_kt) continue;
+      int i0, i1;
+      if (P.flavour == KLLM_FLAVOUR_LLAMA2) {
+        i0 = 2 * pr, i1 = 2 * pr + 1;
+      } else {
+        i0 = pr, i1 = pr + half;
+      }
+      const float fci = P.sin_cache[static_cast<size_t>(pos) * hs + 2 * pr];
+      const float fcr = P.cos_cache[static_cast<size_t>(pos) * hs + 2 * pr];
+      if (hh < kv_mul) {
+        const float* qg = P.q + static_cast<size_t>(grp * kv_mul + hh) * hs;
+        const float x0 = __ldcg(qg + i0), x1 = __ldcg(qg + i1);
+        q_s[hh * hs + i0] = __fmaf_rn(fcr, x0, -__fmul_rn(fci, x1));
+        q_s[hh * hs + i1] = __fmaf_rn(fci, x0, __fmul_rn(fcr, x1));
+      } else {
+        const float* kg = P.k_raw + grp * hs;
+        const float x0 = __ldcg(kg + i0), x1 = __ldcg(kg + i1);
+        const float r0 = __fmaf_rn(fcr, x0, -__fmul_rn(fci, x1));
+        const float r1 = __fmaf_rn(fci, x0, __fmul_rn(fcr, x1));
+        k_s[i0] = r0;
+        k_s[i1] = r1;
+        kcache[(static_cast<size_t>(i0 >> 2) * seq_len + pos) * 4 + (i0 & 3)] = r0;
+        kcache[(static_cast<size_t>(i1 >> 2) * seq_len + pos) * 4 + (i1 & 3)] = r1;
+      }
+    }
+    consumer_sync();
+    if (j < pl.n_kt) {
+      // K tile: warp w takes timesteps [w*tpw, (w+1)*tpw) of the tile, lane = timestep; the
+      // timestep's key row sits in registers while the group's heads are walked.
       const int t0 = j * g.tk;
       const int nt = min(g.tk, pos - t0);
-      const float4* tile = reinterpret_cast<const float4*>(stages + static_cast<size_t>(ring.slot) * P.stage_bytes);
-      float sc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int c = 0; c < (hs >> 2); ++c) {
-        const float4 qv = q4[c];
-        const float4* kc = tile + c * g.tk + lane;
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          if (m < km) {
-            const float4 kv = kc[32 * m];
-            float s = sc[m];
-            s = __fmaf_rn(kv.x, qv.x, s);
-            s = __fmaf_rn(kv.y, qv.y, s);
-            s = __fmaf_rn(kv.z, qv.z, s);
-            s = __fmaf_rn(kv.w, qv.w, s);
-            sc[m] = s;
-          }
-        }
-      }
-#pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int t = lane + 32 * m;
-        if (m < km && t < nt) score[t0 + t] = __fmul_rn(sc[m], scale);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[ring.slot]);
-    }
-    ring.advance(S);
-  }
-  if (tid == kConsumerThreads - 1) {  // t == pos from the freshly rotated key
-    const float4* k4 = reinterpret_cast<const float4*>(k_s);
-    float s = 0.0f;
-    for (int c = 0; c < (hs >> 2); ++c) {
-      const float4 kv = k4[c];
-      const float4 qv = q4[c];
-      s = __fmaf_rn(kv.x, qv.x, s);
-      s = __fmaf_rn(kv.y, qv.y, s);
-      s = __fmaf_rn(kv.z, qv.z, s);
-      s = __fmaf_rn(kv.w, qv.w, s);
-    }
-    score[pos] = __fmul_rn(s, scale);
-  }
-  consumer_sync();
-  if (stamp) stamp[1] = global_ns();
-
-  // ---- softmax, mha_kernel.cu:7-45 (256 strided lanes + cub block-reduce order) -----------------
-  const int size = pos + 1;
-  float max_val = tid < size ? score[tid] : -FLT_MAX;
-  for (int i = tid + kConsumerThreads; i < size; i += kConsumerThreads) max_val = fmaxf(max_val, score[i]);
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) max_val = fmaxf(max_val, __shfl_xor_sync(kFull, max_val, off));
-  if (lane == 0) s_warp[warp] = max_val;
-  consumer_sync();
-  max_val = s_warp[0];
-#pragma unroll
-  for (int w = 1; w < kNW; ++w) max_val = fmaxf(max_val, s_warp[w]);
-  consumer_sync();
-
-  float sum = 0.0f;
-  for (int i = tid; i < size; i += kConsumerThreads) {
-    const float e = expf(score[i] - max_val);
-    score[i] = e;
-    sum += e;
-  }
-  sum = warp_tree_sum(sum);
-  if (lane == 0) s_warp[warp] = sum;
-  consumer_sync();
-  if (tid == 0) {
-    float total = s_warp[0];
-#pragma unroll
-    for (int w = 1; w < kNW; ++w) total = __fadd_rn(total, s_warp[w]);
-    *s_bcast = total;
-  }
-  consumer_sync();
-  sum = *s_bcast;
-  for (int i = tid; i < size; i += kConsumerThreads) score[i] = score[i] / sum;
-  consumer_sync();
-  if (stamp) stamp[7] = global_ns();
-
-  // ---- weighted value sum, mha_kernel.cu:97-109: one FFMA chain per output element.  Warp s owns
-  // slab s (sw output dims) and all of its V tiles, in timestep order.
-  const int n_vt = ceil_div(pos, g.tv);
-  float value = 0.0f;
-  for (int j = 0; j < n_vt; ++j) {
-    for (int sl = 0; sl < g.slabs; ++sl) {
+      const int tpw = g.tk / kNW;
+      const int tl = warp * tpw + lane;
       mbar_wait(&full_bar[ring.slot], ring.parity);
-      if (sl == warp) {
-        const int t0 = j * g.tv;
-        const int nt = min(g.tv, pos - t0);
-        if (lane < g.sw) {
-          const float* vt = reinterpret_cast<const float*>(stages + static_cast<size_t>(ring.slot) * P.stage_bytes) + lane;
-          const float* pr = score + t0;
-          int tt = 0;
-          if ((reinterpret_cast<uintptr_t>(pr) & 15) == 0) {
-            const float4* pr4 = reinterpret_cast<const float4*>(pr);
-#pragma unroll 2
-            for (; tt + 4 <= nt; tt += 4) {
-              const float4 p4 = pr4[tt >> 2];
-              value = __fmaf_rn(p4.x, vt[(tt + 0) * g.sw], value);
-              value = __fmaf_rn(p4.y, vt[(tt + 1) * g.sw], value);
-              value = __fmaf_rn(p4.z, vt[(tt + 2) * g.sw], value);
-              value = __fmaf_rn(p4.w, vt[(tt + 3) * g.sw], value);
-            }
+      if (lane < tpw && tl < nt) {
+        const float4* tile = reinterpret_cast<const float4*>(stages + static_cast<size_t>(ring.slot) * P.stage_bytes);
+        for (int hh = 0; hh < kv_mul; ++hh) {
+          const float4* q4 = reinterpret_cast<const float4*>(q_s + hh * hs);
+          float sc = 0.0f;
+#pragma unroll 4
+          for (int c = 0; c < (hs >> 2); ++c) {
+            const float4 kv = tile[c * g.tk + tl];
+            const float4 qv = q4[c];
+            sc = __fmaf_rn(kv.x, qv.x, sc);
+            sc = __fmaf_rn(kv.y, qv.y, sc);
+            sc = __fmaf_rn(kv.z, qv.z, sc);
+            sc = __fmaf_rn(kv.w, qv.w, sc);
           }
-          for (; tt < nt; ++tt) value = __fmaf_rn(pr[tt], vt[tt * g.sw], value);
+          P.score[static_cast<size_t>(grp * kv_mul + hh) * seq_len + t0 + tl] = __fmul_rn(sc, scale);
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[ring.slot]);
       }
+      consumer_sync();
+      if (tid == 0) mbar_arrive(&empty_bar[ring.slot]);
+      ring.advance(S);
+    } else {
+      // current position: q . rotated new key, one thread per head
+      if (tid < kv_mul) {
+        const float4* q4 = reinterpret_cast<const float4*>(q_s + tid * hs);
+        const float4* k4 = reinterpret_cast<const float4*>(k_s);
+        float sc = 0.0f;
+        for (int c = 0; c < (hs >> 2); ++c) {
+          const float4 kv = k4[c];
+          const float4 qv = q4[c];
+          sc = __fmaf_rn(kv.x, qv.x, sc);
+          sc = __fmaf_rn(kv.y, qv.y, sc);
+          sc = __fmaf_rn(kv.z, qv.z, sc);
+          sc = __fmaf_rn(kv.w, qv.w, sc);
+        }
+        P.score[static_cast<size_t>(grp * kv_mul + tid) * seq_len + pos] = __fmul_rn(sc, scale);
+      }
+      consumer_sync();
+    }
+    if (tid == 0) red_release_add(P.attn_flags + grp, 1u);  // orders the CTA's score stores (bar.sync above)
+  }
+  if (stamp) stamp[1] = stamp[7] = global_ns();
+  const unsigned flag_need = flag_base + static_cast<unsigned>(pl.n_kt + 1);
+  flag_base = flag_need;
+
+  // ================= step B: softmax + weighted values =================
+  const int need = (pos + 1 + 3) & ~3;
+  const bool p_in_smem = static_cast<long long>(pl.hpc) * need <= (P.xbuf_bytes >> 2);
+  for (int item = cta; item < pl.items_b; item += G) {
+    const int grp = item / (g.slabs * pl.nchunks);
+    const int sl = (item / pl.nchunks) % g.slabs;
+    const int ck = item % pl.nchunks;
+    const int h_local = ck * pl.hpc + warp;
+    const bool active = warp < pl.hpc && h_local < kv_mul;
+    const int head = grp * kv_mul + h_local;
+    const size_t head_block = (static_cast<size_t>(ph.layer) * kv_heads + grp) * seq_len * hs;
+    const float* vslab = P.value_cache + head_block + static_cast<size_t>(sl) * seq_len * g.sw;
+    if (tid == 0) {
+      while (static_cast<int>(ld_acquire_u32(P.attn_flags + grp) - flag_need) < 0) {
+      }
+    }
+    consumer_sync();  // also: previous item done with the workspace
+    float* prob = nullptr;
+    float v_pos = 0.f;
+    if (active) {
+      float* srow = P.score + static_cast<size_t>(head) * seq_len;
+      prob = p_in_smem ? (ws + static_cast<size_t>(warp) * need) : srow;
+      if (lane < g.sw) v_pos = __ldcg(vslab + static_cast<size_t>(pos) * g.sw + lane);
+      // ---- softmax, mha_kernel.cu:7-45: 256 strided lanes, cub BlockReduce order; this warp
+      // carries virtual lane (l + 32 w) in acc[w].
+      const int size = pos + 1;
+      float mx = -FLT_MAX;
+      for (int i = lane; i < size; i += 32) {
+        const float v = __ldcg(srow + i);
+        prob[i] = v;
+        mx = fmaxf(mx, v);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, off));
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int base = 0; base < size; base += 256) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const int i = base + 32 * w + lane;
+          if (i < size) {
+            const float e = expf(prob[i] - mx);
+            prob[i] = e;
+            acc[w] += e;
+          }
+        }
+      }
+      float total = warp_tree_sum(acc[0]);
+#pragma unroll
+      for (int w = 1; w < 8; ++w) total = __fadd_rn(total, warp_tree_sum(acc[w]));
+      total = __shfl_sync(kFull, total, 0);
+      for (int i = lane; i < size; i += 32) prob[i] = prob[i] / total;
+      __syncwarp();
+    }
+    if (stamp) stamp[7] = global_ns();
+    // ---- weighted value sum, mha_kernel.cu:97-109: one FFMA chain per output element; the
+    // CTA's warps (one head each) share the slab's V tiles.
+    float value = 0.0f;
+    for (int jv = 0; jv < pl.n_vt; ++jv) {
+      const int t0 = jv * g.tv;
+      const int nt = min(g.tv, pos - t0);
+      mbar_wait(&full_bar[ring.slot], ring.parity);
+      if (active && lane < g.sw) {
+        const float* vt = reinterpret_cast<const float*>(stages + static_cast<size_t>(ring.slot) * P.stage_bytes) + lane;
+        const float* pr = prob + t0;
+        int tt = 0;
+        if ((reinterpret_cast<uintptr_t>(pr) & 15) == 0) {
+          const float4* pr4 = reinterpret_cast<const float4*>(pr);
+#pragma unroll 2
+          for (; tt + 4 <= nt; tt += 4) {
+            const float4 p4 = pr4[tt >> 2];
+            value = __fmaf_rn(p4.x, vt[(tt + 0) * g.sw], value);
+            value = __fmaf_rn(p4.y, vt[(tt + 1) * g.sw], value);
+            value = __fmaf_rn(p4.z, vt[(tt + 2) * g.sw], value);
+            value = __fmaf_rn(p4.w, vt[(tt + 3) * g.sw], value);
+          }
+        }
+        for (; tt < nt; ++tt) value = __fmaf_rn(pr[tt], vt[tt * g.sw], value);
+      }
+      consumer_sync();
+      if (tid == 0) mbar_arrive(&empty_bar[ring.slot]);
       ring.advance(S);
     }
-  }
-  if (warp < g.slabs && lane < g.sw) {
-    value = __fmaf_rn(score[pos], v_pos, value);
-    P.attn_out[static_cast<size_t>(head) * hs + warp * g.sw + lane] = value;
+    if (active && lane < g.sw) {
+      value = __fmaf_rn(prob[pos], v_pos, value);
+      P.attn_out[static_cast<size_t>(head) * hs + sl * g.sw + lane] = value;
+    }
   }
 }
 
@@ -282,9 +324,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
                                          : nullptr;
         if (pstamp) pstamp[4] = global_ns();
         if (ph.kind == kPhaseAttention) {
-          if (cta < P.head_num && ppos > 0) {
-            // rows t < pos of this head: final since the previous token.  Order the async-proxy
-            // reads after the grid barrier that closed the previous token's attention phase.
+          const AttnPlan pl = attn_plan(P, ppos);
+          if (ppos > 0) {
+            // rows t < pos: final since the previous token.  Order the async-proxy reads after the
+            // grid barrier that closed the previous token's attention phase.
             if (tok > 0 && lane == 0) {
               const unsigned need = P.barrier_base + static_cast<unsigned>((tok - 1) * P.n_phases + pi + 1) *
                                                          static_cast<unsigned>(G);
@@ -295,12 +338,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
             __syncwarp();
             const int hs = P.head_size;
             const AttnGeom g = attn_geom(P);
-            const int kvh = cta / P.kv_mul;
-            const size_t head_block = (static_cast<size_t>(ph.layer) * (P.kv_dim / hs) + kvh) * P.seq_len * hs;
-            const float* kbase = P.key_cache + head_block;
-            const float* vbase = P.value_cache + head_block;
-            const int n_kt = ceil_div(ppos, g.tk);
-            for (int j = 0; j < n_kt; ++j) {
+            const int kv_heads = P.kv_dim / hs;
+            for (int item = cta; item < pl.items_a; item += G) {
+              const int grp = item / (pl.n_kt + 1), j = item % (pl.n_kt + 1);
+              if (j == pl.n_kt) continue;
+              const float* kbase = P.key_cache + (static_cast<size_t>(ph.layer) * kv_heads + grp) * P.seq_len * hs;
               const int t0 = j * g.tk;
               const int nt = min(g.tk, ppos - t0);
               mbar_wait(&empty_bar[ring.slot], ring.parity ^ 1u);
@@ -313,17 +355,20 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
                          static_cast<uint32_t>(nt) * 16, &full_bar[ring.slot], policy_kv);
               ring.advance(S);
             }
-            const int n_vt = ceil_div(ppos, g.tv);
-            for (int j = 0; j < n_vt; ++j) {
-              const int t0 = j * g.tv;
-              const int nt = min(g.tv, ppos - t0);
-              for (int sl = 0; sl < g.slabs; ++sl) {
+            for (int item = cta; item < pl.items_b; item += G) {
+              const int grp = item / (g.slabs * pl.nchunks);
+              const int sl = (item / pl.nchunks) % g.slabs;
+              const float* vslab = P.value_cache + (static_cast<size_t>(ph.layer) * kv_heads + grp) * P.seq_len * hs +
+                                   static_cast<size_t>(sl) * P.seq_len * g.sw;
+              for (int jv = 0; jv < pl.n_vt; ++jv) {
+                const int t0 = jv * g.tv;
+                const int nt = min(g.tv, ppos - t0);
                 mbar_wait(&empty_bar[ring.slot], ring.parity ^ 1u);
                 if (lane == 0) {
                   mbar_expect_tx(&full_bar[ring.slot], static_cast<uint32_t>(nt) * g.sw * 4);
                   bulk_g2s(stages + static_cast<size_t>(ring.slot) * P.stage_bytes,
-                           vbase + (static_cast<size_t>(sl) * P.seq_len + t0) * g.sw,
-                           static_cast<uint32_t>(nt) * g.sw * 4, &full_bar[ring.slot], policy_kv);
+                           vslab + static_cast<size_t>(t0) * g.sw, static_cast<uint32_t>(nt) * g.sw * 4,
+                           &full_bar[ring.slot], policy_kv);
                 }
                 __syncwarp();
                 ring.advance(S);
@@ -389,6 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
 
   // =============================== consumer warps ===============================================
   unsigned bar_target = P.barrier_base;
+  unsigned flag_base = 0;  // attn_flags are zeroed before every launch
   int token = P.state->token;
   if (static_cast<unsigned>(token) >= static_cast<unsigned>(P.vocab_size)) token = 0;
   int pos = P.state->pos;
@@ -414,8 +460,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
 
       if (ph.kind == kPhaseAttention) {
         if (stamp) stamp[1] = stamp[6] = stamp[7] = stamp[0];
-        if (cta < P.head_num)
-          attention_phase(P, ph, cta, pos, xs, s_warp, &s_bcast, stages, full_bar, empty_bar, ring, stamp);
+        attention_phase(P, ph, cta, G, pos, xs, stages, full_bar, empty_bar, ring, flag_base, stamp);
         if (stamp) stamp[2] = global_ns();
         grid_barrier(P.barrier, bar_target, G);
         if (stamp) stamp[3] = global_ns();
@@ -625,7 +670,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   // ---- shared memory plan -----------------------------------------------------------------------
   const int max_in = std::max(std::max(dim, hid), q_rows);
   int xbuf = max_in * 4;
-  const int attn_ws = 2 * hs * 4;
+  const int attn_ws = (m.kv_mul + 1) * hs * 4;
   xbuf = std::max(xbuf, attn_ws);
   xbuf = (xbuf + 127) & ~127;
   const int budget = max_smem - xbuf - 2048;  // static smem + slack
@@ -778,6 +823,8 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   cudaMemcpyAsync(d_phases_, ph.data(), sizeof(Phase) * ph.size(), cudaMemcpyHostToDevice, stream);
   if (cudaMalloc(&d_barrier_, 128) != cudaSuccess) return static_cast<int>(cudaErrorMemoryAllocation);
   cudaMemsetAsync(d_barrier_, 0, 128, stream);
+  n_kv_heads_ = kvd / hs;
+  if (cudaMalloc(&d_flags_, sizeof(unsigned) * n_kv_heads_) != cudaSuccess) return static_cast<int>(cudaErrorMemoryAllocation);
   if (cudaMalloc(&d_arg_val_, sizeof(float) * grid_) != cudaSuccess ||
       cudaMalloc(&d_arg_idx_, sizeof(int) * grid_) != cudaSuccess)
     return static_cast<int>(cudaErrorMemoryAllocation);
@@ -800,6 +847,8 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
 void MegaEngine::destroy() {
   if (d_phases_) cudaFree(d_phases_);
   if (d_barrier_) cudaFree(d_barrier_);
+  if (d_flags_) cudaFree(d_flags_);
+  d_flags_ = nullptr;
   if (d_arg_val_) cudaFree(d_arg_val_);
   if (d_arg_idx_) cudaFree(d_arg_idx_);
   d_phases_ = nullptr;
@@ -850,6 +899,9 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
   P.arg_idx = static_cast<int*>(d_arg_idx_);
   P.prof = prof_dev;
   P.prof_token = prof_token;
+  P.attn_flags = static_cast<unsigned*>(d_flags_);
+  cudaError_t me = cudaMemsetAsync(d_flags_, 0, sizeof(unsigned) * n_kv_heads_, stream_);
+  if (me != cudaSuccess) return static_cast<int>(me);
   void* args[] = {&P};
   cudaError_t e = cudaLaunchCooperativeKernel(kernel_, dim3(grid_), dim3(mega::kThreads), args,
                                               smem_bytes_, stream_);

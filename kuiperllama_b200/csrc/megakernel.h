@@ -73,6 +73,7 @@ struct Params {
   int max_steps;
   unsigned* barrier;
   unsigned barrier_base;
+  unsigned* attn_flags;  // [kv_heads] finished step-A items per kv group (zeroed per launch)
   float* arg_val;
   int* arg_idx;
   // optional phase timeline of one token: prof[(cta * n_phases + phase) * 4 + k], k = phase
@@ -127,6 +128,8 @@ class MegaEngine {
   void* d_barrier_ = nullptr;
   void* d_arg_val_ = nullptr;
   void* d_arg_idx_ = nullptr;
+  void* d_flags_ = nullptr;
+  int n_kv_heads_ = 0;
   int grid_ = 0, stages_ = 0, stage_bytes_ = 0, xbuf_bytes_ = 0, n_phases_ = 0, attn_tk_ = 0, attn_tv_ = 0;
   const void* kernel_ = nullptr;
   int n_barriers_per_token_ = 0;

@@ -64,6 +64,11 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -98,8 +103,11 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
   target += grid;
   if (threadIdx.x == 0) {
     red_release_add(counter, 1u);
-    while (static_cast<int>(ld_acquire_u32(counter) - target) < 0) {
+    // poll with relaxed loads (an acquire load invalidates L1 on every iteration), then one
+    // acquire fence orders everything after the barrier
+    while (static_cast<int>(ld_relaxed_u32(counter) - target) < 0) {
     }
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   consumer_sync();
 }

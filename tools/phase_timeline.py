@@ -55,11 +55,10 @@ def main():
     print(f"# producer lead (consumer enters phase - producer finished issuing it), us: "
           + " ".join(f"{nm}={np.median(lead[40:, [l * 5 + k for l in range(1, L)]]):.2f}" for k, nm in enumerate(names) if k != 1))
     ai = [l * 5 + 1 for l in range(L)]
-    H = shape.head_num
-    sa = st[:H][:, ai, :]
-    print("# attention CTAs (us, median): rope %.2f | scores %.2f | softmax %.2f | values %.2f" % (
-        np.median(sa[:, :, 6] - sa[:, :, 0]), np.median(sa[:, :, 1] - sa[:, :, 6]),
-        np.median(sa[:, :, 7] - sa[:, :, 1]), np.median(sa[:, :, 2] - sa[:, :, 7])))
+    sa = st[:, ai, :]
+    print("# attention (us): step A scores, median over CTAs %.2f / max %.2f | step B CTAs: flag wait + softmax %.2f | values %.2f" % (
+        np.median(sa[:, :, 1] - sa[:, :, 0]), (sa[:, :, 1] - sa[:, :, 0]).max(axis=0).mean(),
+        (sa[:, :, 7] - sa[:, :, 1]).max(axis=0).mean(), (sa[:, :, 2] - sa[:, :, 7]).max(axis=0).mean()))
     print(f"# sum of phase durations: {dur.sum():.1f} us; barrier_min = time the LAST arriving CTA spends in the barrier")
 
 
