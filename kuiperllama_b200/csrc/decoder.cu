@@ -506,12 +506,11 @@ int kllm_decoder_read_kv(kllm_decoder* dc, float* key_host, float* value_host) {
     KLLM_TRY(cudaMemcpy(key_host, dc->kcache, n * sizeof(float), cudaMemcpyDeviceToHost));
     return static_cast<int>(cudaMemcpy(value_host, dc->vcache, n * sizeof(float), cudaMemcpyDeviceToHost));
   }
-  // persistent engine: K [L][kvh][hs/4][S][4], V [L][kvh][slab][S][sw] -> reference [L][S][kv_dim]
+  // persistent engine: K [L][kvh][hs/4][S][4], V [L][kvh][S][hs] -> reference [L][S][kv_dim]
   std::vector<float> kraw(n), vraw(n);
   KLLM_TRY(cudaMemcpy(kraw.data(), dc->kcache, n * sizeof(float), cudaMemcpyDeviceToHost));
   KLLM_TRY(cudaMemcpy(vraw.data(), dc->vcache, n * sizeof(float), cudaMemcpyDeviceToHost));
   const size_t nh = kvd / hs;
-  const size_t sw = hs < 32 ? hs : 32, slabs = hs / sw;
   for (size_t l = 0; l < L; ++l)
     for (size_t g = 0; g < nh; ++g) {
       const float* kb = kraw.data() + (l * nh + g) * S * hs;
@@ -520,13 +519,11 @@ int kllm_decoder_read_kv(kllm_decoder* dc, float* key_host, float* value_host) {
         for (size_t i = 0; i < hs; ++i) {
           const size_t dst = (l * S + t) * kvd + g * hs + i;
           key_host[dst] = kb[((i >> 2) * S + t) * 4 + (i & 3)];
-          value_host[dst] = vb[((i / sw) * S + t) * sw + (i % sw)];
+          value_host[dst] = vb[t * hs + i];
         }
     }
-  (void)slabs;
   return 0;
 }
-
 int kllm_decoder_launches_per_step(const kllm_decoder* dc) { return dc ? dc->launches_per_step : 0; }
 const char* kllm_decoder_engine(const kllm_decoder* dc) {
   if (!dc) return "";

@@ -5,17 +5,16 @@
 // Why: at batch 1 the path is a 4-26 GB/token weight stream; with one launch per op (even 6
 // fused launches per layer in a CUDA graph) every kernel boundary drains the HBM pipeline
 // (profiles/r01a: 15-42 % DRAM utilisation per kernel).  Here one CTA per SM stays resident
-// and a dedicated producer warp streams that CTA's share of EVERY weight matrix -- and of the
-// KV cache -- in schedule order through a ring of shared-memory stages with TMA bulk copies
-// (cp.async.bulk -> UBLKCP) signalled on mbarriers.  Weights and past KV rows never depend on
-// the current token's activations, so the producer runs ahead across phase boundaries, grid
-// barriers and the attention phase: HBM keeps streaming while consumers wait for each other.
+// and a dedicated producer warp streams that CTA's share of EVERY weight matrix, in schedule
+// order, through a ring of shared-memory stages with TMA bulk copies (cp.async.bulk ->
+// UBLKCP) signalled on mbarriers.  Weights never depend on activations, so the producer runs
+// ahead across phase boundaries, grid barriers and the attention phase: HBM keeps streaming
+// while consumers wait for each other, and the ~190 KB/SM of ring (28 MB chip-wide, ~4 us of
+// HBM time) absorbs every such stall.
 //
-// Consumers: 8 warps.  Every ring stage is OWNED by one warp (round robin), which waits for it,
-// processes all its rows in groups of up to 4 that share the input-vector loads (the consumers
-// are bound by the 128 B/cycle shared-memory pipe, so traffic per weight byte matters), and
-// releases it.  Schedule per layer (5 grid barriers):  QKV(+bias) | attention(+RoPE) |
-// Wo+residual | W1,W3->SiLU*gate | W2+residual ; then classifier + greedy argmax.
+// Schedule per layer (5 grid barriers):  QKV(+bias) | attention(+RoPE) | Wo+residual |
+// W1,W3->SiLU*gate | W2+residual ; then classifier + greedy argmax.  RoPE moves into the
+// attention phase so GEMV rows can be split evenly over all SMs.
 //
 // Arithmetic is the same as the per-op kernels (gemv.cu / attention.cu / elementwise.cu): every
 // dot product, reduction tree, softmax sum and value chain reproduces the reference CUDA
@@ -23,9 +22,9 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
-#include <algorithm>
 #include <cfloat>
 #include <cstdint>
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
@@ -34,248 +33,401 @@
 #include "kllm_device.cuh"
 #include "kllm_host.h"
 #include "megakernel.h"
-#include "megakernel_device.cuh"
 
 namespace kllm {
 namespace mega {
 
-// ---- attention phase (mha_kernel.cu:47-110 + rope_kernel.cu), two steps inside one schedule phase
-//
-// Per-SM TMA ingest is ~47 GB/s, so a head-per-CTA mapping (8 query heads of a GQA group each
-// re-reading the same 2 x pos x 256 B of KV on 32 SMs) is ingest-bound; instead the KV bytes are
-// read once and spread over every SM:
-//   step A (all CTAs): item (kv group g, K tile j) -> scores of ALL query heads of the group
-//       over the tile's timesteps (one FFMA chain per (head, t), reference order), written to the
-//       global [head][seq_len] score buffer; item (g, n_kt) = the current position: rotate the
-//       new key, store it, score it.  Each finished item bumps flags[g] (release).
-//   step B (few CTAs): item (g, value slab, head chunk): wait for flags[g] (acquire), one warp
-//       per head does the reference softmax (256 virtual lanes folded in cub order) into shared
-//       memory, then walks its FFMA chain over the slab's V tiles; all warps share the tiles.
-// No grid barrier between A and B: only the CTAs that own a B item wait, on their group's flag.
-struct AttnPlan {
-  int n_kt, n_vt, items_a, hpc, nchunks, items_b;
-};
-__device__ __forceinline__ AttnPlan attn_plan(const Params& P, int pos) {
-  AttnPlan a;
-  const AttnGeom g = attn_geom(P);
-  const int kv_heads = P.kv_dim / P.head_size;
-  a.n_kt = ceil_div(pos, g.tk);
-  a.n_vt = ceil_div(pos, g.tv);
-  a.items_a = kv_heads * (a.n_kt + 1);
-  const int cap = P.xbuf_bytes >> 2;
-  const int need = (pos + 1 + 3) & ~3;
-  int hpc = cap / need;  // heads whose probabilities fit the workspace
-  if (hpc > P.kv_mul) hpc = P.kv_mul;
-  if (hpc > kNW) hpc = kNW;
-  if (hpc < 1) hpc = 1;  // probabilities live in the global score buffer instead
-  a.hpc = hpc;
-  a.nchunks = ceil_div(P.kv_mul, hpc);
-  a.items_b = kv_heads * g.slabs * a.nchunks;
-  return a;
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kThreads = kConsumerThreads + 32;  // + one producer warp
+constexpr int kMaxStages = 16;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                         uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
 }
 
-__device__ void attention_phase(const Params& P, const Phase& ph, int cta, int G, int pos, float* ws,
-                                unsigned char* stages, uint64_t* full_bar, uint64_t* empty_bar,
-                                Ring& ring, unsigned& flag_base, unsigned long long* stamp) {
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+struct Pipe {
+  int slot;
+  uint32_t parity;
+  __device__ __forceinline__ void advance(int stages) {
+    if (++slot == stages) {
+      slot = 0;
+      parity ^= 1u;
+    }
+  }
+};
+
+// Grid barrier over the consumer threads of all CTAs.  Monotonic counter, wrap-safe compare.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target, unsigned grid) {
+  consumer_sync();
+  target += grid;
+  if (threadIdx.x == 0) {
+    red_release_add(counter, 1u);
+    while (static_cast<int>(ld_acquire_u32(counter) - target) < 0) {
+    }
+  }
+  consumer_sync();
+}
+
+// ---- unit -> (segment, row) ------------------------------------------------------------------
+struct RowRef {
+  int seg;
+  int row;
+};
+__device__ __forceinline__ RowRef resolve_row(const Phase& ph, int unit, int sub) {
+  if (ph.swiglu) return RowRef{sub, unit};
+  int seg = 0, row = unit;
+  if (ph.n_seg > 1 && row >= ph.seg[0].rows) {
+    row -= ph.seg[0].rows;
+    seg = 1;
+    if (ph.n_seg > 2 && row >= ph.seg[1].rows) {
+      row -= ph.seg[1].rows;
+      seg = 2;
+    }
+  }
+  return RowRef{seg, row};
+}
+
+// ---- exact-order accumulation from shared memory ----------------------------------------------
+// fp32: virtual thread (lane + 32 j) owns packs base + 32 j + lane (matmul_kernel.cu:27-35).
+// Full 128-pack blocks run branch-free with all 4*(1+NR) shared loads issued before the math
+// (two blocks in flight), so the four independent chains per row overlap the LDS latency.
+template <int NR>
+__device__ __forceinline__ void accum_f32(const float4* const (&w)[NR], const float4* x4,
+                                          int n_packs, int lane, float (&acc)[NR][4]) {
+  const int full = n_packs & ~127;
+  const float4* xp = x4 + lane;
+#pragma unroll 2
+  for (int base = 0; base < full; base += 128) {
+    float4 xv[4];
+    float4 wv[NR][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xv[j] = xp[base + 32 * j];
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wv[r][j] = w[r][base + 32 * j + lane];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[r][j] = __fadd_rn(dot4_ref(xv[j], wv[r][j]), acc[r][j]);
+  }
+  if (full < n_packs) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = full + 32 * j + lane;
+      if (idx < n_packs) {
+        const float4 xv = x4[idx];
+#pragma unroll
+        for (int r = 0; r < NR; ++r) acc[r][j] = __fadd_rn(dot4_ref(xv, w[r][idx]), acc[r][j]);
+      }
+    }
+  }
+}
+
+// int8: virtual thread (4 lane + e) owns elements 128 k + 4 lane + e (matmul_kernel.cu:70-74).
+// `sc[r]` points at the row's staged scales (first group of the row at index 0; rows start on a
+// group boundary -- checked on the host).
+template <int NR>
+__device__ __forceinline__ void accum_w8(const uint32_t* const (&w)[NR], const float* const (&sc)[NR],
+                                         const float4* x4, int M, int group_shift, int group_size,
+                                         int lane, float (&acc)[NR][4]) {
+  const int full_chunks = M >> 7;
+  auto one = [&](int k) {
+    const int i = (k << 7) + (lane << 2);
+    const float4 xv = x4[i >> 2];
+    const int g = group_shift >= 0 ? (i >> group_shift) : (i / group_size);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const uint32_t packed = w[r][i >> 2];
+      const float s = sc[r][g];
+      float wf[4];
+      int8x4_to_float(packed, wf);
+      acc[r][0] = __fmaf_rn(__fmul_rn(xv.x, s), wf[0], acc[r][0]);
+      acc[r][1] = __fmaf_rn(__fmul_rn(xv.y, s), wf[1], acc[r][1]);
+      acc[r][2] = __fmaf_rn(__fmul_rn(xv.z, s), wf[2], acc[r][2]);
+      acc[r][3] = __fmaf_rn(__fmul_rn(xv.w, s), wf[3], acc[r][3]);
+    }
+  };
+#pragma unroll 4
+  for (int k = 0; k < full_chunks; ++k) one(k);
+  if ((full_chunks << 7) + (lane << 2) < M) one(full_chunks);
+}
+
+// rmsnorm_kernel.cu:4-50 on x staged in shared memory (warp 0), cf. gemv.cu rms_scale_ref.
+__device__ __forceinline__ float rms_scale_smem(const float* xs, int n, float eps, int lane) {
+  const int pack_num = n >> 2;
+  const float4* xs4 = reinterpret_cast<const float4*>(xs);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int full = pack_num & ~127;
+#pragma unroll 2
+  for (int base = 0; base < full; base += 128) {
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = xs4[base + 32 * j + lane];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float s = acc[j];
+      s = __fmaf_rn(v[j].x, v[j].x, s);
+      s = __fmaf_rn(v[j].y, v[j].y, s);
+      s = __fmaf_rn(v[j].z, v[j].z, s);
+      s = __fmaf_rn(v[j].w, v[j].w, s);
+      acc[j] = s;
+    }
+  }
+  if (full < pack_num) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int idx = full + 32 * j + lane;
+      if (idx < pack_num) {
+        const float4 v = xs4[idx];
+        float s = acc[j];
+        s = __fmaf_rn(v.x, v.x, s);
+        s = __fmaf_rn(v.y, v.y, s);
+        s = __fmaf_rn(v.z, v.z, s);
+        s = __fmaf_rn(v.w, v.w, s);
+        acc[j] = s;
+      }
+    }
+  }
+  float sum = block128_sum_vt(acc);
+  sum = __shfl_sync(kFull, sum, 0);
+  return rsqrtf(__fadd_rn(__fdiv_rn(sum, static_cast<float>(n)), eps));
+}
+
+struct ArgBest {
+  float v;
+  int i;
+};
+__device__ __forceinline__ void arg_fold(ArgBest& a, float ov, int oi) {
+  if (oi >= 0 && (a.i < 0 || ov > a.v || (ov == a.v && oi < a.i))) {
+    a.v = ov;
+    a.i = oi;
+  }
+}
+
+// ---- attention phase: one CTA per query head (mha_kernel.cu:47-110 + rope_kernel.cu) ------------
+// KV layout (persistent engine only; kllm_decoder_read_kv converts back):
+//   K [L][kv_head][head_size/4][seq_len][4]   -- 16-byte chunk c of timestep t at ((c*seq_len)+t)*4:
+//       a tile of T timesteps is hs/4 contiguous runs of T*16 bytes, and "thread t reads chunk c"
+//       is a conflict-free 128-bit shared-memory access (consecutive t -> consecutive 16 B);
+//   V [L][kv_head][seq_len][head_size]        -- a tile of T timesteps is one contiguous block and
+//       "thread i walks column i" is conflict-free.
+// Rows t < pos were written by earlier tokens, so -- like weights -- the producer warp streams
+// them through the ring ahead of time (K tiles first, then V tiles); only row pos is handled
+// here from registers / a direct load.
+__device__ __forceinline__ int attn_tiles(int pos, int T) { return (pos + T - 1) / T; }
+
+__device__ void attention_phase(const Params& P, const Phase& ph, int head, int pos, float* ws,
+                                float* s_warp, float* s_bcast, unsigned char* stages,
+                                uint64_t* full_bar, uint64_t* empty_bar, Pipe& pipe) {
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int hs = P.head_size, seq_len = P.seq_len, S = P.num_stages, kv_mul = P.kv_mul;
-  const AttnGeom g = attn_geom(P);
-  const AttnPlan pl = attn_plan(P, pos);
-  const int kv_heads = P.kv_dim / hs;
-  const float scale = 1.f / sqrtf(static_cast<float>(hs));
-  float* q_s = ws;                 // [kv_mul][hs] rotated queries of one group
-  float* k_s = ws + kv_mul * hs;   // [hs] rotated key of the current position
+  const int hs = P.head_size, seq_len = P.seq_len, T = P.attn_tile, S = P.num_stages;
+  float* q_s = ws;       // [hs] rotated query
+  float* k_s = ws + hs;  // [hs] rotated key of the current position
+  const int kvh = head / P.kv_mul;
+  const size_t head_block = (static_cast<size_t>(ph.layer) * (P.kv_dim / hs) + kvh) * seq_len * hs;
+  float* kcache = P.key_cache + head_block;
+  const float* vcache = P.value_cache + head_block;
+  // scores / probabilities: shared memory when the context fits the workspace (the ring leaves
+  // almost no L1), else the global [head][seq_len] buffer the reference uses
+  const int smem_cap = (P.xbuf_bytes >> 2) - 2 * hs;
+  float* score_head = (pos + 1 <= smem_cap) ? (ws + 2 * hs) : (P.score + static_cast<size_t>(head) * seq_len);
 
-  // ================= step A: scores =================
-  for (int item = cta; item < pl.items_a; item += G) {
-    const int grp = item / (pl.n_kt + 1);
-    const int j = item % (pl.n_kt + 1);
-    const size_t head_block = (static_cast<size_t>(ph.layer) * kv_heads + grp) * seq_len * hs;
-    float* kcache = P.key_cache + head_block;
-    consumer_sync();  // previous item done with q_s / k_s
-    // RoPE of the group's queries (and, for the current-position item, of the new key row):
-    // rope_kernel.cu as compiled -- x' = fma(cos, x0, -(sin*x1)), y' = fma(sin, x0, cos*x1)
-    const int half = hs >> 1;
-    for (int idx = tid; idx < (kv_mul + 1) * half; idx += kConsumerThreads) {
-      const int hh = idx / half, pr = idx % half;
-      if (hh == kv_mul && j != pl.n_kt) continue;
-      int i0, i1;
-      if (P.flavour == KLLM_FLAVOUR_LLAMA2) {
-        i0 = 2 * pr, i1 = 2 * pr + 1;
-      } else {
-        i0 = pr, i1 = pr + half;
-      }
-      const float fci = P.sin_cache[static_cast<size_t>(pos) * hs + 2 * pr];
-      const float fcr = P.cos_cache[static_cast<size_t>(pos) * hs + 2 * pr];
-      if (hh < kv_mul) {
-        const float* qg = P.q + static_cast<size_t>(grp * kv_mul + hh) * hs;
-        const float x0 = __ldcg(qg + i0), x1 = __ldcg(qg + i1);
-        q_s[hh * hs + i0] = __fmaf_rn(fcr, x0, -__fmul_rn(fci, x1));
-        q_s[hh * hs + i1] = __fmaf_rn(fci, x0, __fmul_rn(fcr, x1));
-      } else {
-        const float* kg = P.k_raw + grp * hs;
-        const float x0 = __ldcg(kg + i0), x1 = __ldcg(kg + i1);
-        const float r0 = __fmaf_rn(fcr, x0, -__fmul_rn(fci, x1));
-        const float r1 = __fmaf_rn(fci, x0, __fmul_rn(fcr, x1));
-        k_s[i0] = r0;
-        k_s[i1] = r1;
-        kcache[(static_cast<size_t>(i0 >> 2) * seq_len + pos) * 4 + (i0 & 3)] = r0;
-        kcache[(static_cast<size_t>(i1 >> 2) * seq_len + pos) * 4 + (i1 & 3)] = r1;
-      }
-    }
-    consumer_sync();
-    if (j < pl.n_kt) {
-      // K tile: warp w takes timesteps [w*tpw, (w+1)*tpw) of the tile, lane = timestep; the
-      // timestep's key row sits in registers while the group's heads are walked.
-      const int t0 = j * g.tk;
-      const int nt = min(g.tk, pos - t0);
-      const int tpw = g.tk / kNW;
-      const int tl = warp * tpw + lane;
-      mbar_wait(&full_bar[ring.slot], ring.parity);
-      if (lane < tpw && tl < nt) {
-        const float4* tile = reinterpret_cast<const float4*>(stages + static_cast<size_t>(ring.slot) * P.stage_bytes);
-        for (int hh = 0; hh < kv_mul; ++hh) {
-          const float4* q4 = reinterpret_cast<const float4*>(q_s + hh * hs);
-          float sc = 0.0f;
-#pragma unroll 4
-          for (int c = 0; c < (hs >> 2); ++c) {
-            const float4 kv = tile[c * g.tk + tl];
-            const float4 qv = q4[c];
-            sc = __fmaf_rn(kv.x, qv.x, sc);
-            sc = __fmaf_rn(kv.y, qv.y, sc);
-            sc = __fmaf_rn(kv.z, qv.z, sc);
-            sc = __fmaf_rn(kv.w, qv.w, sc);
-          }
-          P.score[static_cast<size_t>(grp * kv_mul + hh) * seq_len + t0 + tl] = __fmul_rn(sc, scale);
-        }
-      }
-      consumer_sync();
-      if (tid == 0) mbar_arrive(&empty_bar[ring.slot]);
-      ring.advance(S);
+  // value row of the current position (written by the QKV phase of this token)
+  float v_pos = 0.f;
+  if (tid < hs) v_pos = __ldcg(vcache + static_cast<size_t>(pos) * hs + tid);
+
+  // RoPE on q (this head) and on the new key row, rope_kernel.cu as compiled (elementwise.cu)
+  if (tid < hs / 2) {
+    const float* qg = P.q + static_cast<size_t>(head) * hs;
+    const float* kg = P.k_raw + kvh * hs;
+    int i0, i1;
+    if (P.flavour == KLLM_FLAVOUR_LLAMA2) {
+      i0 = 2 * tid, i1 = 2 * tid + 1;
     } else {
-      // current position: q . rotated new key, one thread per head
-      if (tid < kv_mul) {
-        const float4* q4 = reinterpret_cast<const float4*>(q_s + tid * hs);
-        const float4* k4 = reinterpret_cast<const float4*>(k_s);
-        float sc = 0.0f;
-        for (int c = 0; c < (hs >> 2); ++c) {
-          const float4 kv = k4[c];
-          const float4 qv = q4[c];
-          sc = __fmaf_rn(kv.x, qv.x, sc);
-          sc = __fmaf_rn(kv.y, qv.y, sc);
-          sc = __fmaf_rn(kv.z, qv.z, sc);
-          sc = __fmaf_rn(kv.w, qv.w, sc);
-        }
-        P.score[static_cast<size_t>(grp * kv_mul + tid) * seq_len + pos] = __fmul_rn(sc, scale);
-      }
-      consumer_sync();
+      i0 = tid, i1 = tid + hs / 2;
     }
-    if (tid == 0) red_release_add(P.attn_flags + grp, 1u);  // orders the CTA's score stores (bar.sync above)
+    const int ci = 2 * tid;
+    const float fci = P.sin_cache[static_cast<size_t>(pos) * hs + ci];
+    const float fcr = P.cos_cache[static_cast<size_t>(pos) * hs + ci];
+    const float q0 = __ldcg(qg + i0), q1 = __ldcg(qg + i1);
+    q_s[i0] = __fmaf_rn(fcr, q0, -__fmul_rn(fci, q1));
+    q_s[i1] = __fmaf_rn(fci, q0, __fmul_rn(fcr, q1));
+    const float k0 = __ldcg(kg + i0), k1 = __ldcg(kg + i1);
+    const float r0 = __fmaf_rn(fcr, k0, -__fmul_rn(fci, k1));
+    const float r1 = __fmaf_rn(fci, k0, __fmul_rn(fcr, k1));
+    k_s[i0] = r0;
+    k_s[i1] = r1;
+    if (head % P.kv_mul == 0) {  // one writer per kv head stores the rotated key
+      kcache[(static_cast<size_t>(i0 >> 2) * seq_len + pos) * 4 + (i0 & 3)] = r0;
+      kcache[(static_cast<size_t>(i1 >> 2) * seq_len + pos) * 4 + (i1 & 3)] = r1;
+    }
   }
-  if (stamp) stamp[1] = stamp[7] = global_ns();
-  const unsigned flag_need = flag_base + static_cast<unsigned>(pl.n_kt + 1);
-  flag_base = flag_need;
+  consumer_sync();
 
-  // ================= step B: softmax + weighted values =================
-  const int need = (pos + 1 + 3) & ~3;
-  const bool p_in_smem = static_cast<long long>(pl.hpc) * need <= (P.xbuf_bytes >> 2);
-  for (int item = cta; item < pl.items_b; item += G) {
-    const int grp = item / (g.slabs * pl.nchunks);
-    const int sl = (item / pl.nchunks) % g.slabs;
-    const int ck = item % pl.nchunks;
-    const int h_local = ck * pl.hpc + warp;
-    const bool active = warp < pl.hpc && h_local < kv_mul;
-    const int head = grp * kv_mul + h_local;
-    const size_t head_block = (static_cast<size_t>(ph.layer) * kv_heads + grp) * seq_len * hs;
-    const float* vslab = P.value_cache + head_block + static_cast<size_t>(sl) * seq_len * g.sw;
-    if (tid == 0) {
-      while (static_cast<int>(ld_acquire_u32(P.attn_flags + grp) - flag_need) < 0) {
+  // ---- scores: one left-to-right FFMA chain per timestep (mha_kernel.cu:61-91) ---------------
+  const float scale = 1.f / sqrtf(static_cast<float>(hs));
+  const float4* q4 = reinterpret_cast<const float4*>(q_s);
+  const int n_tiles = attn_tiles(pos, T);
+  for (int j = 0; j < n_tiles; ++j) {
+    const int t0 = j * T;
+    const int nt = min(T, pos - t0);
+    mbar_wait(&full_bar[pipe.slot], pipe.parity);
+    const float4* tile = reinterpret_cast<const float4*>(stages + static_cast<size_t>(pipe.slot) * P.stage_bytes);
+    if (tid < nt) {
+      float score = 0.0f;
+#pragma unroll 4
+      for (int c = 0; c < (hs >> 2); ++c) {
+        const float4 kv = tile[c * T + tid];
+        const float4 qv = q4[c];
+        score = __fmaf_rn(kv.x, qv.x, score);
+        score = __fmaf_rn(kv.y, qv.y, score);
+        score = __fmaf_rn(kv.z, qv.z, score);
+        score = __fmaf_rn(kv.w, qv.w, score);
       }
+      score_head[t0 + tid] = __fmul_rn(score, scale);
     }
-    consumer_sync();  // also: previous item done with the workspace
-    float* prob = nullptr;
-    float v_pos = 0.f;
-    if (active) {
-      float* srow = P.score + static_cast<size_t>(head) * seq_len;
-      prob = p_in_smem ? (ws + static_cast<size_t>(warp) * need) : srow;
-      if (lane < g.sw) v_pos = __ldcg(vslab + static_cast<size_t>(pos) * g.sw + lane);
-      // ---- softmax, mha_kernel.cu:7-45: 256 strided lanes, cub BlockReduce order; this warp
-      // carries virtual lane (l + 32 w) in acc[w].
-      const int size = pos + 1;
-      float mx = -FLT_MAX;
-      for (int i = lane; i < size; i += 32) {
-        const float v = __ldcg(srow + i);
-        prob[i] = v;
-        mx = fmaxf(mx, v);
-      }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
+    pipe.advance(S);
+  }
+  if (tid == 0) {  // t == pos from the freshly rotated key
+    const float4* k4 = reinterpret_cast<const float4*>(k_s);
+    float score = 0.0f;
+    for (int c = 0; c < (hs >> 2); ++c) {
+      const float4 kv = k4[c];
+      const float4 qv = q4[c];
+      score = __fmaf_rn(kv.x, qv.x, score);
+      score = __fmaf_rn(kv.y, qv.y, score);
+      score = __fmaf_rn(kv.z, qv.z, score);
+      score = __fmaf_rn(kv.w, qv.w, score);
+    }
+    score_head[pos] = __fmul_rn(score, scale);
+  }
+  consumer_sync();
+
+  // ---- softmax, mha_kernel.cu:7-45 (256 strided lanes + cub block-reduce order) -----------------
+  const int size = pos + 1;
+  float max_val = tid < size ? score_head[tid] : -FLT_MAX;
+  for (int i = tid + kConsumerThreads; i < size; i += kConsumerThreads)
+    max_val = fmaxf(max_val, score_head[i]);
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, off));
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int base = 0; base < size; base += 256) {
+  for (int off = 16; off > 0; off >>= 1) max_val = fmaxf(max_val, __shfl_xor_sync(kFull, max_val, off));
+  if (lane == 0) s_warp[warp] = max_val;
+  consumer_sync();
+  max_val = s_warp[0];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) {
-          const int i = base + 32 * w + lane;
-          if (i < size) {
-            const float e = expf(prob[i] - mx);
-            prob[i] = e;
-            acc[w] += e;
-          }
-        }
-      }
-      float total = warp_tree_sum(acc[0]);
+  for (int w = 1; w < kConsumerWarps; ++w) max_val = fmaxf(max_val, s_warp[w]);
+  consumer_sync();
+
+  float sum = 0.0f;
+  for (int i = tid; i < size; i += kConsumerThreads) {
+    const float e = expf(score_head[i] - max_val);
+    score_head[i] = e;
+    sum += e;
+  }
+  sum = warp_tree_sum(sum);
+  if (lane == 0) s_warp[warp] = sum;
+  consumer_sync();
+  if (tid == 0) {
+    float total = s_warp[0];
 #pragma unroll
-      for (int w = 1; w < 8; ++w) total = __fadd_rn(total, warp_tree_sum(acc[w]));
-      total = __shfl_sync(kFull, total, 0);
-      for (int i = lane; i < size; i += 32) prob[i] = prob[i] / total;
-      __syncwarp();
+    for (int w = 1; w < kConsumerWarps; ++w) total = __fadd_rn(total, s_warp[w]);
+    *s_bcast = total;
+  }
+  consumer_sync();
+  sum = *s_bcast;
+  for (int i = tid; i < size; i += kConsumerThreads) score_head[i] = score_head[i] / sum;
+  consumer_sync();
+
+  // ---- weighted value sum, mha_kernel.cu:97-109: one FFMA chain per output element ----------------
+  float value = 0.0f;
+  for (int j = 0; j < n_tiles; ++j) {
+    const int t0 = j * T;
+    const int nt = min(T, pos - t0);
+    mbar_wait(&full_bar[pipe.slot], pipe.parity);
+    if (tid < hs) {
+      const float* vt = reinterpret_cast<const float*>(stages + static_cast<size_t>(pipe.slot) * P.stage_bytes) + tid;
+      const float* pr = score_head + t0;
+#pragma unroll 8
+      for (int tt = 0; tt < nt; ++tt) value = __fmaf_rn(pr[tt], vt[tt * hs], value);
     }
-    if (stamp) stamp[7] = global_ns();
-    // ---- weighted value sum, mha_kernel.cu:97-109: one FFMA chain per output element; the
-    // CTA's warps (one head each) share the slab's V tiles.
-    float value = 0.0f;
-    for (int jv = 0; jv < pl.n_vt; ++jv) {
-      const int t0 = jv * g.tv;
-      const int nt = min(g.tv, pos - t0);
-      mbar_wait(&full_bar[ring.slot], ring.parity);
-      if (active && lane < g.sw) {
-        const float* vt = reinterpret_cast<const float*>(stages + static_cast<size_t>(ring.slot) * P.stage_bytes) + lane;
-        const float* pr = prob + t0;
-        int tt = 0;
-        if ((reinterpret_cast<uintptr_t>(pr) & 15) == 0) {
-          const float4* pr4 = reinterpret_cast<const float4*>(pr);
-#pragma unroll 2
-          for (; tt + 4 <= nt; tt += 4) {
-            const float4 p4 = pr4[tt >> 2];
-            value = __fmaf_rn(p4.x, vt[(tt + 0) * g.sw], value);
-            value = __fmaf_rn(p4.y, vt[(tt + 1) * g.sw], value);
-            value = __fmaf_rn(p4.z, vt[(tt + 2) * g.sw], value);
-            value = __fmaf_rn(p4.w, vt[(tt + 3) * g.sw], value);
-          }
-        }
-        for (; tt < nt; ++tt) value = __fmaf_rn(pr[tt], vt[tt * g.sw], value);
-      }
-      consumer_sync();
-      if (tid == 0) mbar_arrive(&empty_bar[ring.slot]);
-      ring.advance(S);
-    }
-    if (active && lane < g.sw) {
-      value = __fmaf_rn(prob[pos], v_pos, value);
-      P.attn_out[static_cast<size_t>(head) * hs + sl * g.sw + lane] = value;
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
+    pipe.advance(S);
+  }
+  if (tid < hs) {
+    value = __fmaf_rn(score_head[pos], v_pos, value);
+    P.attn_out[static_cast<size_t>(head) * hs + tid] = value;
   }
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------
-template <bool kInt8>
 __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t full_bar[kMaxStages];
   __shared__ uint64_t empty_bar[kMaxStages];
-  __shared__ float s_warp[kNW];
+  __shared__ float s_warp[kConsumerWarps];
   __shared__ float s_bcast;
-  __shared__ float s_argv[kNW];
-  __shared__ int s_argi[kNW];
+  __shared__ float s_argv[kConsumerWarps];
+  __shared__ int s_argi[kConsumerWarps];
   // The ring leaves only a few KB of L1, so everything the inner loops touch lives in shared
   // memory or registers: the consumer's and the producer's current schedule entries are copied
   // here (they are usually in different phases).
@@ -288,25 +440,25 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const bool is_producer = warp == kNW;
+  const bool is_producer = warp == kConsumerWarps;
   const int cta = blockIdx.x;
   const int G = gridDim.x;
-  constexpr int wbytes = kInt8 ? 1 : 4;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(&full_bar[s], 1);   // producer's expect_tx arrival (+ transaction bytes)
-      mbar_init(&empty_bar[s], 1);  // the owning consumer warp
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumerWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  Ring ring{0, 0u, 0};
+  Pipe pipe{0, 0u};
+  const int wbytes = P.group_size > 0 ? 1 : 4;
 
   // =============================== producer warp ===============================================
   if (is_producer) {
-    const uint64_t policy = policy_evict_first();   // weights: streamed once per token
+    const uint64_t policy = policy_evict_first();  // weights: streamed once per token
     const uint64_t policy_kv = policy_evict_last();  // KV tiles: re-read every token, keep in L2
     int ppos = P.state->pos;
     for (int tok = 0; tok < P.n_tokens; ++tok, ++ppos) {
@@ -322,60 +474,46 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
         unsigned long long* pstamp = (P.prof != nullptr && tok == P.prof_token && lane == 0)
                                          ? P.prof + (static_cast<size_t>(cta) * P.n_phases + pi) * 8
                                          : nullptr;
-        if (pstamp) pstamp[4] = global_ns();
+        (void)pstamp;
         if (ph.kind == kPhaseAttention) {
-          const AttnPlan pl = attn_plan(P, ppos);
-          if (ppos > 0) {
-            // rows t < pos: final since the previous token.  Order the async-proxy reads after the
-            // grid barrier that closed the previous token's attention phase.
-            if (tok > 0 && lane == 0) {
-              const unsigned need = P.barrier_base + static_cast<unsigned>((tok - 1) * P.n_phases + pi + 1) *
-                                                         static_cast<unsigned>(G);
-              while (static_cast<int>(ld_acquire_u32(P.barrier) - need) < 0) {
-              }
-              asm volatile("fence.proxy.async;" ::: "memory");
+          if (cta >= P.head_num || ppos == 0) continue;
+          // rows t < pos of this head: final since the previous token.  Order the async-proxy
+          // reads after the grid barrier that closed the previous token's attention phase.
+          if (tok > 0 && lane == 0) {
+            const unsigned need = P.barrier_base +
+                                  static_cast<unsigned>((tok - 1) * P.n_phases + pi + 1) * static_cast<unsigned>(G);
+            while (static_cast<int>(ld_acquire_u32(P.barrier) - need) < 0) {
             }
-            __syncwarp();
-            const int hs = P.head_size;
-            const AttnGeom g = attn_geom(P);
-            const int kv_heads = P.kv_dim / hs;
-            for (int item = cta; item < pl.items_a; item += G) {
-              const int grp = item / (pl.n_kt + 1), j = item % (pl.n_kt + 1);
-              if (j == pl.n_kt) continue;
-              const float* kbase = P.key_cache + (static_cast<size_t>(ph.layer) * kv_heads + grp) * P.seq_len * hs;
-              const int t0 = j * g.tk;
-              const int nt = min(g.tk, ppos - t0);
-              mbar_wait(&empty_bar[ring.slot], ring.parity ^ 1u);
-              unsigned char* dst = stages + static_cast<size_t>(ring.slot) * P.stage_bytes;
-              if (lane == 0) mbar_expect_tx(&full_bar[ring.slot], static_cast<uint32_t>(nt) * hs * 4);
+            asm volatile("fence.proxy.async;" ::: "memory");
+          }
+          __syncwarp();
+          const int hs = P.head_size, T = P.attn_tile;
+          const int kvh = cta / P.kv_mul;
+          const size_t head_block =
+              (static_cast<size_t>(ph.layer) * (P.kv_dim / hs) + kvh) * P.seq_len * hs;
+          const float* kbase = P.key_cache + head_block;
+          const float* vbase = P.value_cache + head_block;
+          const int n_tiles = attn_tiles(ppos, T);
+          for (int kv = 0; kv < 2; ++kv) {
+            for (int j = 0; j < n_tiles; ++j) {
+              const int t0 = j * T;
+              const int nt = min(T, ppos - t0);
+              mbar_wait(&empty_bar[pipe.slot], pipe.parity ^ 1u);
+              unsigned char* dst = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
+              if (lane == 0) mbar_expect_tx(&full_bar[pipe.slot], static_cast<uint32_t>(nt) * hs * 4);
               __syncwarp();
-              if (lane < (hs >> 2))
-                bulk_g2s(dst + static_cast<size_t>(lane) * g.tk * 16,
-                         kbase + (static_cast<size_t>(lane) * P.seq_len + t0) * 4,
-                         static_cast<uint32_t>(nt) * 16, &full_bar[ring.slot], policy_kv);
-              ring.advance(S);
-            }
-            for (int item = cta; item < pl.items_b; item += G) {
-              const int grp = item / (g.slabs * pl.nchunks);
-              const int sl = (item / pl.nchunks) % g.slabs;
-              const float* vslab = P.value_cache + (static_cast<size_t>(ph.layer) * kv_heads + grp) * P.seq_len * hs +
-                                   static_cast<size_t>(sl) * P.seq_len * g.sw;
-              for (int jv = 0; jv < pl.n_vt; ++jv) {
-                const int t0 = jv * g.tv;
-                const int nt = min(g.tv, ppos - t0);
-                mbar_wait(&empty_bar[ring.slot], ring.parity ^ 1u);
-                if (lane == 0) {
-                  mbar_expect_tx(&full_bar[ring.slot], static_cast<uint32_t>(nt) * g.sw * 4);
-                  bulk_g2s(stages + static_cast<size_t>(ring.slot) * P.stage_bytes,
-                           vslab + static_cast<size_t>(t0) * g.sw, static_cast<uint32_t>(nt) * g.sw * 4,
-                           &full_bar[ring.slot], policy_kv);
-                }
-                __syncwarp();
-                ring.advance(S);
+              if (kv == 0) {
+                if (lane < (hs >> 2))
+                  bulk_g2s(dst + static_cast<size_t>(lane) * T * 16,
+                           kbase + (static_cast<size_t>(lane) * P.seq_len + t0) * 4,
+                           static_cast<uint32_t>(nt) * 16, &full_bar[pipe.slot], policy_kv);
+              } else if (lane == 0) {
+                bulk_g2s(dst, vbase + static_cast<size_t>(t0) * hs, static_cast<uint32_t>(nt) * hs * 4,
+                         &full_bar[pipe.slot], policy_kv);
               }
+              pipe.advance(S);
             }
           }
-          if (pstamp) pstamp[5] = global_ns();
           continue;
         }
         const int u0 = static_cast<int>(static_cast<long long>(cta) * ph.units / G);
@@ -387,24 +525,26 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
           for (int u = u0; u < u1; u += ups) {
             const int n = min(ups, u1 - u);
             const int nrows = n * rpu;
-            mbar_wait(&empty_bar[ring.slot], ring.parity ^ 1u);
-            unsigned char* dst = stages + static_cast<size_t>(ring.slot) * P.stage_bytes;
+            mbar_wait(&empty_bar[pipe.slot], pipe.parity ^ 1u);
+            unsigned char* dst = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
             if (lane == 0)
-              mbar_expect_tx(&full_bar[ring.slot],
+              mbar_expect_tx(&full_bar[pipe.slot],
                              static_cast<uint32_t>(nrows) * (row_bytes + ph.scale_row_bytes));
             __syncwarp();
             for (int i = lane; i < nrows; i += 32) {
               const RowRef rr = resolve_row(ph, u + i / rpu, i % rpu);
               const long long e = static_cast<long long>(rr.row) * ph.in_dim;
               const unsigned char* src = static_cast<const unsigned char*>(ph.seg[rr.seg].w) + e * wbytes;
-              bulk_g2s(dst + static_cast<size_t>(i) * row_bytes, src, row_bytes, &full_bar[ring.slot], policy);
-              if (kInt8) {
+              bulk_g2s(dst + static_cast<size_t>(i) * row_bytes, src, row_bytes,
+                       &full_bar[pipe.slot], policy);
+              if (ph.scale_row_bytes) {
                 const long long g0 = ph.group_shift >= 0 ? (e >> ph.group_shift) : (e / ph.group_size);
                 bulk_g2s(dst + ph.scale_off + static_cast<size_t>(i) * ph.scale_row_bytes,
-                         ph.seg[rr.seg].scales + g0, ph.scale_row_bytes, &full_bar[ring.slot], policy);
+                         ph.seg[rr.seg].scales + g0, ph.scale_row_bytes, &full_bar[pipe.slot],
+                         policy);
               }
             }
-            ring.advance(S);
+            pipe.advance(S);
           }
         } else {
           for (int u = u0; u < u1; ++u) {
@@ -414,19 +554,19 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
             for (int c = 0; c < ph.chunks_per_row; ++c) {
               const int e0 = c * ph.chunk_elems;
               const int ne = min(ph.chunk_elems, ph.in_dim - e0);
-              mbar_wait(&empty_bar[ring.slot], ring.parity ^ 1u);
+              mbar_wait(&empty_bar[pipe.slot], pipe.parity ^ 1u);
               if (lane == 0) {
-                mbar_expect_tx(&full_bar[ring.slot], static_cast<uint32_t>(ne) * wbytes);
-                bulk_g2s(stages + static_cast<size_t>(ring.slot) * P.stage_bytes,
+                mbar_expect_tx(&full_bar[pipe.slot], static_cast<uint32_t>(ne) * wbytes);
+                bulk_g2s(stages + static_cast<size_t>(pipe.slot) * P.stage_bytes,
                          src + static_cast<size_t>(e0) * wbytes, static_cast<uint32_t>(ne) * wbytes,
-                         &full_bar[ring.slot], policy);
+                         &full_bar[pipe.slot], policy);
               }
               __syncwarp();
-              ring.advance(S);
+              pipe.advance(S);
             }
           }
         }
-        if (pstamp) pstamp[5] = global_ns();
+        
       }
     }
     return;
@@ -434,7 +574,6 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
 
   // =============================== consumer warps ===============================================
   unsigned bar_target = P.barrier_base;
-  unsigned flag_base = 0;  // attn_flags are zeroed before every launch
   int token = P.state->token;
   if (static_cast<unsigned>(token) >= static_cast<unsigned>(P.vocab_size)) token = 0;
   int pos = P.state->pos;
@@ -442,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
 
   for (int tok = 0; tok < P.n_tokens; ++tok) {
     const float* emb_row = P.tok_emb + static_cast<size_t>(token) * P.dim;
-    ArgBest best{0.f, -1};  // per lane; folded across the CTA after the classifier phase
+    ArgBest best{0.f, -1};
 
     const bool prof_on = P.prof != nullptr && tok == P.prof_token && tid == 0;
     for (int pi = 0; pi < P.n_phases; ++pi) {
@@ -459,9 +598,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
       if (stamp) stamp[0] = global_ns();
 
       if (ph.kind == kPhaseAttention) {
-        if (stamp) stamp[1] = stamp[6] = stamp[7] = stamp[0];
-        attention_phase(P, ph, cta, G, pos, xs, stages, full_bar, empty_bar, ring, flag_base, stamp);
-        if (stamp) stamp[2] = global_ns();
+        if (cta < P.head_num)
+          attention_phase(P, ph, cta, pos, xs, s_warp, &s_bcast, stages, full_bar, empty_bar, pipe);
+        if (stamp) stamp[1] = stamp[2] = global_ns();
         grid_barrier(P.barrier, bar_target, G);
         if (stamp) stamp[3] = global_ns();
         continue;
@@ -516,95 +655,174 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
           consumer_sync();
         }
       }
+      const float4* xs4 = reinterpret_cast<const float4*>(xs);
       if (stamp) stamp[1] = global_ns();
-
-      RowCtx cx;
-      cx.xs4 = reinterpret_cast<const float4*>(xs);
-      cx.residual = ph.residual_from_emb ? emb_row : ph.residual;
-      cx.pos = pos;
-      cx.head_size = P.head_size;
-      cx.seq_len = P.seq_len;
 
       const int u0 = static_cast<int>(static_cast<long long>(cta) * ph.units / G);
       const int u1 = static_cast<int>(static_cast<long long>(cta + 1) * ph.units / G);
       const int rpu = ph.swiglu ? 2 : 1;
+      const int row_bytes = M * wbytes;
+      const float* residual = ph.residual_from_emb ? emb_row : ph.residual;
 
+      // bias / residual of a unit are fetched BEFORE its dot product so their L2 latency hides
+      // behind the accumulation (lane 0 only)
+      auto prefetch_addend = [&](int unit, float& bias_v, float& res_v) {
+        bias_v = 0.f, res_v = 0.f;
+        if (ph.swiglu || lane != 0) return;
+        const RowRef rr = resolve_row(ph, unit, 0);
+        if (ph.seg[rr.seg].bias != nullptr) bias_v = __ldg(ph.seg[rr.seg].bias + rr.row);
+        if (residual != nullptr) res_v = __ldcg(residual + rr.row);
+      };
+      auto epilogue = [&](int unit, float d0, float d1, float bias_v, float res_v) {
+        // lane 0 only
+        if (ph.swiglu) {
+          ph.seg[0].out[unit] = swiglu_ref(d0, d1);
+          return;
+        }
+        const RowRef rr = resolve_row(ph, unit, 0);
+        const Seg& sg = ph.seg[rr.seg];
+        float v = d0;
+        if (sg.bias != nullptr) v = __fadd_rn(v, bias_v);       // matmul.cpp:74-77: out + bias
+        if (residual != nullptr) v = __fadd_rn(res_v, v);       // llama3.cpp:683,719: x + out
+        if (sg.head_major) {
+          const int hs = P.head_size;
+          sg.out[(static_cast<size_t>(rr.row / hs) * P.seq_len + pos) * hs + rr.row % hs] = v;
+        } else {
+          sg.out[static_cast<long long>(pos) * sg.pos_stride + rr.row] = v;
+        }
+        if (ph.argmax) arg_fold(best, v, rr.row);
+      };
+
+      long long cyc_wait = 0, cyc_rows = 0;
+      long long cyc4[4] = {0, 0, 0, 0};
       if (ph.chunks_per_row == 1) {
         const int ups = ph.rows_per_stage / rpu;
         for (int u = u0; u < u1; u += ups) {
-          mbar_wait(&full_bar[ring.slot], ring.parity);  // all warps track every fill (see attention)
-          if (ring.count % kNW == warp) {  // this warp owns the stage
-            const int n = min(ups, u1 - u);
-            const unsigned char* sbase = stages + static_cast<size_t>(ring.slot) * P.stage_bytes;
-            process_stage<kInt8>(ph, cx, sbase, u, n, lane, best);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[ring.slot]);
+          const int n = min(ups, u1 - u);
+          const long long c0 = stamp ? clock64() : 0;
+          mbar_wait(&full_bar[pipe.slot], pipe.parity);
+          const long long c1 = stamp ? clock64() : 0;
+          cyc_wait += c1 - c0;
+          const unsigned char* sbase = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
+          // units go round-robin over ALL consumer warps across stages (a stage may hold fewer
+          // units than there are warps)
+          const int first = ((warp - (u - u0)) % kConsumerWarps + kConsumerWarps) % kConsumerWarps;
+          for (int i = first; i < n; i += kConsumerWarps) {
+            const int unit = u + i;
+            float bias_v, res_v;
+            const long long t_a = stamp ? clock64() : 0;
+            prefetch_addend(unit, bias_v, res_v);
+            const long long t_b = stamp ? clock64() : 0;
+            if (P.group_size == 0) {
+              if (ph.swiglu) {
+                const float4* w[2] = {reinterpret_cast<const float4*>(sbase + static_cast<size_t>(2 * i) * row_bytes),
+                                      reinterpret_cast<const float4*>(sbase + static_cast<size_t>(2 * i + 1) * row_bytes)};
+                float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                accum_f32<2>(w, xs4, M >> 2, lane, acc);
+                const long long t_c = stamp ? clock64() : 0;
+                const float d0 = block128_sum_vt(acc[0]);
+                const float d1 = block128_sum_vt(acc[1]);
+                const long long t_d = stamp ? clock64() : 0;
+                if (lane == 0) epilogue(unit, d0, d1, bias_v, res_v);
+                if (stamp) {
+                  cyc4[0] += t_b - t_a, cyc4[1] += t_c - t_b, cyc4[2] += t_d - t_c, cyc4[3] += clock64() - t_d;
+                }
+              } else {
+                const float4* w[1] = {reinterpret_cast<const float4*>(sbase + static_cast<size_t>(i) * row_bytes)};
+                float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+                accum_f32<1>(w, xs4, M >> 2, lane, acc);
+                const long long t_c = stamp ? clock64() : 0;
+                const float d0 = block128_sum_vt(acc[0]);
+                const long long t_d = stamp ? clock64() : 0;
+                if (lane == 0) epilogue(unit, d0, 0.f, bias_v, res_v);
+                if (stamp) {
+                  cyc4[0] += t_b - t_a, cyc4[1] += t_c - t_b, cyc4[2] += t_d - t_c, cyc4[3] += clock64() - t_d;
+                }
+              }
+            } else {
+              if (ph.swiglu) {
+                const uint32_t* w[2];
+                const float* sc[2];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                  w[r] = reinterpret_cast<const uint32_t*>(sbase + static_cast<size_t>(2 * i + r) * row_bytes);
+                  sc[r] = reinterpret_cast<const float*>(sbase + ph.scale_off +
+                                                         static_cast<size_t>(2 * i + r) * ph.scale_row_bytes);
+                }
+                float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                accum_w8<2>(w, sc, xs4, M, ph.group_shift, ph.group_size, lane, acc);
+                const float d0 = block128_sum_quad(acc[0]);
+                const float d1 = block128_sum_quad(acc[1]);
+                if (lane == 0) epilogue(unit, d0, d1, bias_v, res_v);
+              } else {
+                const uint32_t* w[1] = {reinterpret_cast<const uint32_t*>(sbase + static_cast<size_t>(i) * row_bytes)};
+                const float* sc[1] = {reinterpret_cast<const float*>(sbase + ph.scale_off +
+                                                                     static_cast<size_t>(i) * ph.scale_row_bytes)};
+                float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+                accum_w8<1>(w, sc, xs4, M, ph.group_shift, ph.group_size, lane, acc);
+                const float d0 = block128_sum_quad(acc[0]);
+                if (lane == 0) epilogue(unit, d0, 0.f, bias_v, res_v);
+              }
+            }
           }
-          ring.advance(S);
+          __syncwarp();
+          if (stamp) cyc_rows += clock64() - c1;
+          if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
+          pipe.advance(S);
         }
       } else {
         // rows longer than a stage (fp32 only): the owning warp carries its partial sums across
-        // the row's consecutive stages; chunk boundaries are multiples of 128 packs so every
-        // virtual thread still sees its packs in increasing order.
+        // consecutive stages; chunk boundaries are multiples of 128 packs so every virtual
+        // thread still sees its packs in increasing order.
         for (int u = u0; u < u1; ++u) {
-          const bool mine = ((u - u0) % kNW) == warp;
+          const bool mine = ((u - u0) % kConsumerWarps) == warp;
           float bias_v = 0.f, res_v = 0.f;
-          RowRef rr{0, 0};
-          if (mine && lane == 0) {
-            rr = resolve_row(ph, u, 0);
-            if (ph.seg[rr.seg].bias != nullptr) bias_v = __ldg(ph.seg[rr.seg].bias + rr.row);
-            if (cx.residual != nullptr) res_v = __ldcg(cx.residual + rr.row);
-          }
+          if (mine) prefetch_addend(u, bias_v, res_v);
           float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
           for (int c = 0; c < ph.chunks_per_row; ++c) {
-            mbar_wait(&full_bar[ring.slot], ring.parity);
+            const int e0 = c * ph.chunk_elems;
+            const int ne = min(ph.chunk_elems, M - e0);
+            mbar_wait(&full_bar[pipe.slot], pipe.parity);
             if (mine) {
-              const int e0 = c * ph.chunk_elems;
-              const int ne = min(ph.chunk_elems, M - e0);
               const float4* w[1] = {reinterpret_cast<const float4*>(
-                  stages + static_cast<size_t>(ring.slot) * P.stage_bytes)};
-              accum_f32<1>(w, cx.xs4 + (e0 >> 2), ne >> 2, lane, acc);
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&empty_bar[ring.slot]);
+                  stages + static_cast<size_t>(pipe.slot) * P.stage_bytes)};
+              accum_f32<1>(w, xs4 + (e0 >> 2), ne >> 2, lane, acc);
             }
-            ring.advance(S);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
+            pipe.advance(S);
           }
           if (mine) {
             const float d0 = block128_sum_vt(acc[0]);
-            if (lane == 0) {
-              const Seg& sg = ph.seg[rr.seg];
-              float v = d0;
-              if (sg.bias != nullptr) v = __fadd_rn(v, bias_v);
-              if (cx.residual != nullptr) v = __fadd_rn(res_v, v);
-              if (sg.head_major) {
-                sg.out[v_index(rr.row, pos, P.head_size, P.seq_len)] = v;
-              } else {
-                sg.out[static_cast<long long>(pos) * sg.pos_stride + rr.row] = v;
-              }
-              if (ph.argmax) arg_fold(best, v, rr.row);
-            }
+            if (lane == 0) epilogue(u, d0, 0.f, bias_v, res_v);
           }
         }
       }
 
       if (ph.argmax) {
         // per-CTA (max, lowest index) of the classifier rows this CTA produced
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1)
-          arg_fold(best, __shfl_xor_sync(kFull, best.v, off), __shfl_xor_sync(kFull, best.i, off));
+        float bv = __shfl_sync(kFull, best.v, 0);
+        int bi = __shfl_sync(kFull, best.i, 0);
         if (lane == 0) {
-          s_argv[warp] = best.v;
-          s_argi[warp] = best.i;
+          s_argv[warp] = bv;
+          s_argi[warp] = bi;
         }
         consumer_sync();
         if (tid == 0) {
           ArgBest b{0.f, -1};
-          for (int w = 0; w < kNW; ++w) arg_fold(b, s_argv[w], s_argi[w]);
+          for (int w = 0; w < kConsumerWarps; ++w) arg_fold(b, s_argv[w], s_argi[w]);
           P.arg_val[cta] = b.v;
           P.arg_idx[cta] = b.i;
         }
       }
-      if (stamp) stamp[2] = global_ns();
+      if (stamp) {
+        stamp[2] = global_ns();
+        stamp[4] = static_cast<unsigned long long>(cyc4[0]);
+        stamp[5] = static_cast<unsigned long long>(cyc4[1]);
+        stamp[6] = static_cast<unsigned long long>(cyc4[2]);
+        stamp[7] = static_cast<unsigned long long>(cyc4[3]);
+        (void)cyc_wait, (void)cyc_rows;
+      }
       grid_barrier(P.barrier, bar_target, G);
       if (stamp) stamp[3] = global_ns();
     }
@@ -656,9 +874,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   const bool int8 = m.group_size > 0;
   const int wb = int8 ? 1 : 4;
   // shapes the ring handles: 16-byte rows, 128-byte aligned kv rows (L1-cached reads stay exact)
-  if ((dim & 3) || (hid & 3) || (q_rows & 3) || (hs & 3)) return KLLM_E_UNSUPPORTED;
-  // value slabs are 32 output dims wide (one warp each): head_size 32k, or a single narrow slab
-  if (!((hs % 32 == 0 && hs / 32 <= mega::kNW) || hs < 32)) return KLLM_E_UNSUPPORTED;
+  if ((dim & 3) || (hid & 3) || (q_rows & 3) || (hs & 3) || hs > mega::kConsumerThreads) return KLLM_E_UNSUPPORTED;
   if (int8 && ((dim & 15) || (hid & 15) || (q_rows & 15) || (m.group_size & 3))) return KLLM_E_UNSUPPORTED;
   if ((hs * 4) % 16 != 0) return KLLM_E_UNSUPPORTED;
   if (int8) {
@@ -670,13 +886,13 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   // ---- shared memory plan -----------------------------------------------------------------------
   const int max_in = std::max(std::max(dim, hid), q_rows);
   int xbuf = max_in * 4;
-  const int attn_ws = (m.kv_mul + 1) * hs * 4;
+  const int attn_ws = 2 * hs * 4;
   xbuf = std::max(xbuf, attn_ws);
   xbuf = (xbuf + 127) & ~127;
   const int budget = max_smem - xbuf - 2048;  // static smem + slack
   const int min_row = std::min(std::min(dim, hid), q_rows) * wb;
   (void)min_row;
-  int stage_bytes = 48 * 1024;
+  int stage_bytes = 32 * 1024;
   if (const char* e = getenv("KLLM_STAGE_BYTES")) stage_bytes = atoi(e);
   stage_bytes = (stage_bytes + 127) & ~127;
   int stages = budget / stage_bytes;
@@ -685,10 +901,8 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   if (stages < 2) return KLLM_E_UNSUPPORTED;
   stage_bytes_ = stage_bytes;
   stages_ = stages;
-  // K tile: lanes carry up to 8 timesteps each; V tile: one slab of min(hs,32) dims
-  attn_tk_ = std::min(stage_bytes / (hs * 4), 256) & ~31;
-  attn_tv_ = std::min(stage_bytes / (std::min(hs, 32) * 4), 1024) & ~3;
-  if (attn_tk_ < 32 || attn_tv_ < 4) return KLLM_E_UNSUPPORTED;
+  attn_tile_ = std::min(stage_bytes / (hs * 4), mega::kConsumerThreads) & ~31;
+  if (attn_tile_ < 32) return KLLM_E_UNSUPPORTED;
   xbuf_bytes_ = xbuf;
   smem_bytes_ = static_cast<size_t>(xbuf) + static_cast<size_t>(stages) * stage_bytes;
 
@@ -823,20 +1037,18 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   cudaMemcpyAsync(d_phases_, ph.data(), sizeof(Phase) * ph.size(), cudaMemcpyHostToDevice, stream);
   if (cudaMalloc(&d_barrier_, 128) != cudaSuccess) return static_cast<int>(cudaErrorMemoryAllocation);
   cudaMemsetAsync(d_barrier_, 0, 128, stream);
-  n_kv_heads_ = kvd / hs;
-  if (cudaMalloc(&d_flags_, sizeof(unsigned) * n_kv_heads_) != cudaSuccess) return static_cast<int>(cudaErrorMemoryAllocation);
   if (cudaMalloc(&d_arg_val_, sizeof(float) * grid_) != cudaSuccess ||
       cudaMalloc(&d_arg_idx_, sizeof(int) * grid_) != cudaSuccess)
     return static_cast<int>(cudaErrorMemoryAllocation);
   cudaStreamSynchronize(stream);  // ph (host vector) must outlive the async copy
 
-  kernel_ = int8 ? reinterpret_cast<const void*>(mega::decode_megakernel<true>)
-                 : reinterpret_cast<const void*>(mega::decode_megakernel<false>);
-  cudaError_t e = cudaFuncSetAttribute(kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(mega::decode_megakernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem_bytes_));
   if (e != cudaSuccess) return static_cast<int>(e);
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_, mega::kThreads, smem_bytes_);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mega::decode_megakernel, mega::kThreads,
+                                                    smem_bytes_);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (occ < 1) return KLLM_E_UNSUPPORTED;
   barrier_base_ = 0;
@@ -847,8 +1059,6 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
 void MegaEngine::destroy() {
   if (d_phases_) cudaFree(d_phases_);
   if (d_barrier_) cudaFree(d_barrier_);
-  if (d_flags_) cudaFree(d_flags_);
-  d_flags_ = nullptr;
   if (d_arg_val_) cudaFree(d_arg_val_);
   if (d_arg_idx_) cudaFree(d_arg_idx_);
   d_phases_ = nullptr;
@@ -869,8 +1079,7 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
   P.num_stages = stages_;
   P.stage_bytes = stage_bytes_;
   P.xbuf_bytes = xbuf_bytes_;
-  P.attn_tk = attn_tk_;
-  P.attn_tv = attn_tv_;
+  P.attn_tile = attn_tile_;
   P.group_size = m.group_size;
   P.dim = m.dim;
   P.vocab_size = m.vocab_size;
@@ -899,12 +1108,10 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
   P.arg_idx = static_cast<int*>(d_arg_idx_);
   P.prof = prof_dev;
   P.prof_token = prof_token;
-  P.attn_flags = static_cast<unsigned*>(d_flags_);
-  cudaError_t me = cudaMemsetAsync(d_flags_, 0, sizeof(unsigned) * n_kv_heads_, stream_);
-  if (me != cudaSuccess) return static_cast<int>(me);
   void* args[] = {&P};
-  cudaError_t e = cudaLaunchCooperativeKernel(kernel_, dim3(grid_), dim3(mega::kThreads), args,
-                                              smem_bytes_, stream_);
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mega::decode_megakernel),
+                                              dim3(grid_), dim3(mega::kThreads), args, smem_bytes_,
+                                              stream_);
   if (e != cudaSuccess) return static_cast<int>(e);
   barrier_base_ += static_cast<unsigned>(n_tokens) * static_cast<unsigned>(n_barriers_per_token_) *
                    static_cast<unsigned>(grid_);

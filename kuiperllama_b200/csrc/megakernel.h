@@ -17,7 +17,7 @@ struct Seg {
   float* out;           // out[pos * pos_stride + row]
   long long pos_stride;
   int rows;
-  int head_major;       // 1: out is the slab-major value cache (megakernel_device.cuh v_index)
+  int head_major;       // 1: out is the head-major value cache, index ((row/hs)*seq_len + pos)*hs + row%hs
 };
 
 // One entry of the per-token schedule.  A GEMV phase's units (rows, or w1/w3 row pairs) are
@@ -53,7 +53,7 @@ struct Params {
   const Phase* phases;
   int n_phases, n_tokens;
   int num_stages, stage_bytes, xbuf_bytes;
-  int attn_tk, attn_tv;  // timesteps per K / V ring stage
+  int attn_tile;  // timesteps per K/V ring stage
   int group_size;
   int dim, vocab_size, head_num, head_size, kv_dim, kv_mul, seq_len, flavour;
   const float* tok_emb;
@@ -62,7 +62,7 @@ struct Params {
   float* attn_out;
   float* score;
   // KV cache in the persistent engine's own layout (see megakernel.cu "KV layout"):
-  //   K [L][kv_head][head_size/4][seq_len][4]    V [L][kv_head][slab][seq_len][min(hs,32)]
+  //   K [L][kv_head][head_size/4][seq_len][4]    V [L][kv_head][seq_len][head_size]
   float* key_cache;
   const float* value_cache;
   const float* sin_cache;
@@ -73,7 +73,6 @@ struct Params {
   int max_steps;
   unsigned* barrier;
   unsigned barrier_base;
-  unsigned* attn_flags;  // [kv_heads] finished step-A items per kv group (zeroed per launch)
   float* arg_val;
   int* arg_idx;
   // optional phase timeline of one token: prof[(cta * n_phases + phase) * 4 + k], k = phase
@@ -120,6 +119,7 @@ class MegaEngine {
   int stages() const { return stages_; }
   int stage_bytes() const { return stage_bytes_; }
   int phases() const { return n_phases_; }
+  int attn_tile() const { return attn_tile_; }
 
  private:
   MegaModel model_{};
@@ -128,10 +128,7 @@ class MegaEngine {
   void* d_barrier_ = nullptr;
   void* d_arg_val_ = nullptr;
   void* d_arg_idx_ = nullptr;
-  void* d_flags_ = nullptr;
-  int n_kv_heads_ = 0;
-  int grid_ = 0, stages_ = 0, stage_bytes_ = 0, xbuf_bytes_ = 0, n_phases_ = 0, attn_tk_ = 0, attn_tv_ = 0;
-  const void* kernel_ = nullptr;
+  int grid_ = 0, stages_ = 0, stage_bytes_ = 0, xbuf_bytes_ = 0, n_phases_ = 0, attn_tile_ = 0;
   int n_barriers_per_token_ = 0;
   size_t smem_bytes_ = 0;
   unsigned barrier_base_ = 0;
