@@ -183,6 +183,10 @@ int kllm_decoder_generate(kllm_decoder* dec, int32_t first_token, int32_t start_
 /* Blocking copies for tests: logits of the last step [vocab]; the KV cache in the REFERENCE
  * layout [layer][seq_len][kv_dim] (llama3.cpp:469-475) whatever the engine keeps internally. */
 int kllm_decoder_logits(kllm_decoder* dec, float* logits_host);
+/* Device pointer to the same logits [vocab] (what the reference keeps in
+ * ModelBufferType::kForwardOutput, llama3.cpp:498-506); valid until the decoder is destroyed,
+ * contents ordered after the last step on the decoder's stream. */
+const float* kllm_decoder_logits_device(const kllm_decoder* dec);
 int kllm_decoder_read_kv(kllm_decoder* dec, float* key_host, float* value_host);
 /* Kernel launches one decode step issues (graph nodes; 1 for the persistent engine). */
 int kllm_decoder_launches_per_step(const kllm_decoder* dec);

@@ -87,6 +87,7 @@ _SIGNATURES = {
     "kllm_decoder_generate": (c_int, [c_void_p, c_int32, c_int32, c_int32, POINTER(c_int32),
                                       POINTER(c_int32)]),
     "kllm_decoder_logits": (c_int, [c_void_p, c_void_p]),
+    "kllm_decoder_logits_device": (c_void_p, [c_void_p]),
     "kllm_decoder_read_kv": (c_int, [c_void_p, c_void_p, c_void_p]),
     "kllm_decoder_launches_per_step": (c_int, [c_void_p]),
     "kllm_decoder_engine": (c_char_p, [c_void_p]),

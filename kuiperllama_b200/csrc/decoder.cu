@@ -497,6 +497,8 @@ int kllm_decoder_logits(kllm_decoder* dc, float* logits_host) {
                                      cudaMemcpyDeviceToHost));
 }
 
+const float* kllm_decoder_logits_device(const kllm_decoder* dc) { return dc ? dc->logits : nullptr; }
+
 int kllm_decoder_read_kv(kllm_decoder* dc, float* key_host, float* value_host) {
   if (!dc || !key_host || !value_host) return KLLM_E_INVALID;
   KLLM_TRY(cudaStreamSynchronize(dc->stream));

@@ -1,0 +1,72 @@
+// Tokenizer "layers" (reference op/encode.h).  Tokenisation is not on the decode hot path and its
+// third-party stack (sentencepiece, re2, abseil, nlohmann_json) is not vendored: with
+// -DKLLM_WITH_SENTENCEPIECE the SentencePiece model is used, otherwise a deterministic id-level
+// stand-in keeps Model::init working for synthetic checkpoints (ids in, "<id>" text out).
+#ifndef KLLM_KUIPER_OP_ENCODE_H_
+#define KLLM_KUIPER_OP_ENCODE_H_
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "layer.h"
+#ifdef KLLM_WITH_SENTENCEPIECE
+#include <sentencepiece_processor.h>
+#endif
+namespace op {
+class EncodeLayerBase : public Layer {
+ public:
+  explicit EncodeLayerBase(std::string token_model_path, bool has_bos, bool has_eos)
+      : Layer(base::DeviceType::kDeviceCPU, LayerType::kLayerEncode, "Encode"),
+        has_bos_(has_bos),
+        has_eos_(has_eos),
+        token_model_path_(std::move(token_model_path)) {}
+  virtual std::vector<int32_t> encode(const std::string& sentence) const = 0;
+  virtual std::string decode(int32_t token_id) const = 0;
+  virtual std::string decode(const std::vector<int32_t>& token_ids) const = 0;
+  virtual bool is_sentence_ending(int32_t token_id) const = 0;
+  virtual int32_t vocab_size() const = 0;
+
+ protected:
+  bool has_bos_ = true;
+  bool has_eos_ = false;
+  std::string token_model_path_;
+};
+
+class SpeEncodeLayer : public EncodeLayerBase {
+ public:
+  explicit SpeEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos);
+  std::vector<int32_t> encode(const std::string& sentence) const override;
+  std::string decode(int32_t token_id) const override;
+  std::string decode(const std::vector<int32_t>& token_ids) const override;
+  bool is_sentence_ending(int32_t token_id) const override;
+  int32_t vocab_size() const override;
+
+ private:
+#ifdef KLLM_WITH_SENTENCEPIECE
+  std::unique_ptr<sentencepiece::SentencePieceProcessor> spe;
+#endif
+  int32_t stub_vocab_ = 32000;
+};
+
+// tiktoken-style BPE front ends (Llama-3 / Qwen2 tokenizer.json).  Stand-in only, see above.
+class BpeEncodeLayer : public EncodeLayerBase {
+ public:
+  explicit BpeEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos);
+  std::vector<int32_t> encode(const std::string& sentence) const override;
+  std::string decode(int32_t token_id) const override;
+  std::string decode(const std::vector<int32_t>& token_ids) const override;
+  bool is_sentence_ending(int32_t token_id) const override;
+  int32_t vocab_size() const override;
+
+ protected:
+  int32_t bos_id_ = -1;
+  int32_t eos_id_ = -1;
+  int32_t num_token_ = 0;
+};
+
+class QwenEncodeLayer : public BpeEncodeLayer {
+ public:
+  explicit QwenEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos);
+};
+}  // namespace op
+#endif

@@ -1,0 +1,94 @@
+// Tokenizer front ends (reference kuiper/source/op/encode.cpp).  See op/encode.h for scope.
+#include "op/encode.h"
+
+#include <fstream>
+#include <sstream>
+
+namespace op {
+namespace {
+// "<12><7>" style text for ids: lossless and obviously synthetic
+std::string ids_to_text(const std::vector<int32_t>& ids) {
+  std::ostringstream os;
+  for (int32_t id : ids) os << '<' << id << '>';
+  return os.str();
+}
+// stand-in encoding: BOS (1) then one id per byte, offset past the control ids
+std::vector<int32_t> bytes_to_ids(const std::string& s, bool bos, bool eos, int32_t vocab) {
+  std::vector<int32_t> ids;
+  if (bos) ids.push_back(1);
+  for (unsigned char c : s) ids.push_back(3 + static_cast<int32_t>(c) % (vocab > 259 ? 256 : 1));
+  if (eos) ids.push_back(2);
+  return ids;
+}
+}  // namespace
+
+SpeEncodeLayer::SpeEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos)
+    : EncodeLayerBase(std::move(token_model_path), has_bos, has_eos) {
+#ifdef KLLM_WITH_SENTENCEPIECE
+  spe = std::make_unique<sentencepiece::SentencePieceProcessor>();
+  auto rc = spe->Load(token_model_path_);
+  if (!rc.ok()) {
+    LOG(FATAL) << "The token model path is not valid, please check the path and type of token model.";
+  }
+#else
+  LOG(INFO) << "SentencePiece support not compiled in: using the id-level stand-in tokenizer for "
+            << token_model_path_;
+#endif
+}
+
+std::vector<int32_t> SpeEncodeLayer::encode(const std::string& sentence) const {
+#ifdef KLLM_WITH_SENTENCEPIECE
+  std::vector<int32_t> ids = spe->EncodeAsIds(sentence);
+  if (has_bos_) ids.insert(ids.begin(), spe->bos_id());
+  if (has_eos_) ids.push_back(spe->eos_id());
+  return ids;
+#else
+  return bytes_to_ids(sentence, has_bos_, has_eos_, stub_vocab_);
+#endif
+}
+
+std::string SpeEncodeLayer::decode(int32_t token_id) const { return decode(std::vector<int32_t>{token_id}); }
+
+std::string SpeEncodeLayer::decode(const std::vector<int32_t>& token_ids) const {
+#ifdef KLLM_WITH_SENTENCEPIECE
+  return spe->DecodeIds(token_ids);
+#else
+  return ids_to_text(token_ids);
+#endif
+}
+
+bool SpeEncodeLayer::is_sentence_ending(int32_t token_id) const {
+#ifdef KLLM_WITH_SENTENCEPIECE
+  return token_id == spe->eos_id();
+#else
+  UNUSED(token_id);
+  return false;  // synthetic checkpoints: always decode the requested number of steps
+#endif
+}
+
+int32_t SpeEncodeLayer::vocab_size() const {
+#ifdef KLLM_WITH_SENTENCEPIECE
+  return spe->GetPieceSize();
+#else
+  return stub_vocab_;
+#endif
+}
+
+BpeEncodeLayer::BpeEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos)
+    : EncodeLayerBase(std::move(token_model_path), has_bos, has_eos) {
+  bos_id_ = 1;
+  eos_id_ = 2;
+  num_token_ = 151936;  // overwritten by the checkpoint header (model.cpp:149)
+  LOG(INFO) << "tiktoken/BPE support is not part of this library: using the id-level stand-in tokenizer.";
+}
+std::vector<int32_t> BpeEncodeLayer::encode(const std::string& sentence) const {
+  return bytes_to_ids(sentence, has_bos_, has_eos_, num_token_);
+}
+std::string BpeEncodeLayer::decode(int32_t token_id) const { return ids_to_text({token_id}); }
+std::string BpeEncodeLayer::decode(const std::vector<int32_t>& token_ids) const { return ids_to_text(token_ids); }
+bool BpeEncodeLayer::is_sentence_ending(int32_t) const { return false; }
+int32_t BpeEncodeLayer::vocab_size() const { return num_token_; }
+
+QwenEncodeLayer::QwenEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos)
+    : BpeEncodeLayer(std::move(token_model_path), has_bos, has_eos) {}
+}  // namespace op
