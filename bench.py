@@ -126,12 +126,13 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel_key):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, or None."""
+def ncu_traffic(workload, kernel_key):
+    """DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture)
+    of a kernel, from the committed summary profiles/dominant_kernel_traffic.json, or None."""
     p = ROOT / "profiles" / "dominant_kernel_traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get(kernel_key)
+            return json.loads(p.read_text()).get(workload, {}).get(kernel_key)
         except Exception:
             return None
     return None
@@ -252,10 +253,16 @@ def run_ours(args, rank, world):
 
     stream = torch.cuda.current_stream()
     stream_ptr = ctypes.c_void_p(stream.cuda_stream)
+    comm = None
+    local = shape  # this rank's share of the model (== shape on one GPU)
     if world > 1:
-        from kuiperllama_b200.tensor_parallel import make_tp_decoder
-        w_full = None
-        dec, w = make_tp_decoder(shape, args.seed, rank, world, stream.cuda_stream)
+        from kuiperllama_b200.tensor_parallel import Comm, local_shape, make_tp_decoder
+        comm = Comm(shape.dim)
+        full = synth_weights(shape, "cuda", args.seed)  # same seed on every rank -> same model
+        dec = make_tp_decoder(shape, full, comm, stream.cuda_stream)
+        w, local = dec.weights, local_shape(shape, world, rank)
+        del full
+        torch.cuda.empty_cache()
     else:
         w = synth_weights(shape, "cuda", args.seed)
         dec = Decoder(shape, w, stream=stream.cuda_stream)
@@ -305,10 +312,17 @@ def run_ours(args, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
     if rank != 0:
+        dec.close()
+        if comm:
+            comm.close()
         return
 
     tok_s = K / (ms / 1e3)
     bytes_tok = shape.weight_bytes_per_token()
+    # what ONE GPU streams per token: its shard of the matmuls + the replicated classifier,
+    # embedding row and norm vectors
+    from kuiperllama_b200.tensor_parallel import weight_bytes_per_token_per_gpu
+    bytes_tok_gpu = weight_bytes_per_token_per_gpu(shape, world, rank)
     peak, peak_src = measured_peaks()
     line = {
         "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": K,
@@ -326,22 +340,41 @@ def run_ours(args, rank, world):
                 "d2h_bytes_per_step": 16},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "step_hbm_frac": {"algorithmic_gbs": bytes_tok * tok_s / 1e9 / world, "peak_gbs": peak,
-                          "frac": bytes_tok * tok_s / 1e9 / world / peak,
-                          "note": "whole decode step incl. attention, per GPU"},
     }
-    if world == 1:
-        algo, sec, n = dominant_kernel_roofline(lib, shape, w, stream_ptr, torch)
-        ach = algo / sec / 1e9
-        line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                            "frac": ach / peak, "traffic": ncu_traffic(args.workload),
-                            "kernel": "gemv_kernel<*,swiglu> (RMSNorm->W1|W3->SiLU*gate)",
-                            "algorithmic_bytes_per_launch": algo, "avg_launch_us": sec * 1e6,
-                            "launches_timed": n, "peak_source": peak_src}
-        if not args.no_cpu_baseline:
-            dec.close()
-            line["cpu_baseline"] = cpu_baseline(shape, w, args.cpu_seconds)
+    if world > 1:
+        line["config"]["tp_comm"] = comm.backend
+        line["config"]["weight_bytes_per_token_per_gpu"] = bytes_tok_gpu
+    engine = dec.engine
+    line["config"]["engine"] = engine
+    algo, sec, n = dominant_kernel_roofline(lib, local, w, stream_ptr, torch)
+    gemv = {"bound": "hbm", "achieved": algo / sec / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": algo / sec / 1e9 / peak, "traffic": ncu_traffic(args.workload, "gemv"),
+            "kernel": "gemv_kernel<*,swiglu> (RMSNorm->W1|W3->SiLU*gate), timed alone",
+            "algorithmic_bytes_per_launch": algo, "avg_launch_us": sec * 1e6,
+            "launches_timed": n, "peak_source": peak_src}
+    if engine == "persistent":
+        # ONE launch of the persistent megakernel decodes all K positions: the dominant (only)
+        # kernel of the step.  Algorithmic bytes per launch = K x bytes per token; its duration is
+        # the event-timed region above (the launch is the only work between the two events).
+        ach = bytes_tok_gpu * K / (ms / 1e3) / 1e9
+        traffic = ncu_traffic(args.workload, "megakernel")
+        line["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                            "traffic": traffic["dram_bytes_per_token"] * K if traffic else None,
+                            "kernel": "decode_megakernel (persistent, whole forward + argmax, %d positions per launch)" % K,
+                            "algorithmic_bytes_per_launch": bytes_tok_gpu * K, "avg_launch_us": ms * 1e3,
+                            "launches_timed": 1, "peak_source": peak_src,
+                            "traffic_source": traffic}
+        line["roofline_fused_gemv_alone"] = gemv
+    else:
+        line["roofline"] = gemv
+        line["step_hbm_frac"] = {"algorithmic_gbs": bytes_tok_gpu * tok_s / 1e9, "peak_gbs": peak,
+                                 "frac": bytes_tok_gpu * tok_s / 1e9 / peak,
+                                 "note": "whole decode step (all launches), per GPU"}
+    if world == 1 and not args.no_cpu_baseline:
+        dec.close()
+        line["cpu_baseline"] = cpu_baseline(shape, w, args.cpu_seconds)
     print(json.dumps(line))
+    sys.stdout.flush()
 
 
 def main():
@@ -350,6 +383,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if world == 1 and args.gpus > 1:  # plain `python bench.py --gpus N`: become the torchrun launch
+        os.execv(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                  f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                                  "--master-port", os.environ.get("MASTER_PORT", "29517"),
+                                  str(Path(__file__).resolve()), *sys.argv[1:]])
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -32,6 +32,7 @@ extern "C" {
 #define KLLM_E_UNSUPPORTED (-2) /* shape outside what the kernels handle */
 #define KLLM_E_STATE (-3)       /* decoder used before/after its valid life cycle */
 #define KLLM_E_NODEVICE (-4)    /* no usable CUDA device */
+#define KLLM_E_COMM (-5)        /* tensor-parallel transport unavailable / collective failed */
 
 /* RoPE pairing / constants = the reference's compile-time flavour (CMakeLists.txt:16-25). */
 #define KLLM_FLAVOUR_LLAMA2 0 /* interleaved pairs, theta 1e4, eps 1e-5 */
@@ -127,6 +128,35 @@ typedef struct {
 
 int kllm_gemv_fused(const kllm_gemv_job* job, void* stream);
 
+/* ---- tensor-parallel exchange --------------------------------------------------------------
+ * Not in the reference (single GPU: llama3.cpp:118 pins device 0); SURVEY.md section 8e.  One
+ * process per GPU; each owns a kllm_comm.  The decoder issues exactly two all-reduces per layer:
+ * after o_proj (before the residual add of llama3.cpp:683-684) and after down_proj (:719).
+ *   KLLM_COMM_PEER: one-shot all-reduce over NVLink peer memory (CUDA IPC), rank-ordered sum,
+ *                   residual add fused; set up = create on every rank, exchange the 64-byte IPC
+ *                   handles out of band, connect, barrier.
+ *   KLLM_COMM_NCCL: ncclAllReduce on the decoder's stream (libnccl dlopen'ed at run time);
+ *                   set up = unique_id on rank 0, broadcast the 128 bytes, create everywhere.  */
+#define KLLM_COMM_PEER 0
+#define KLLM_COMM_NCCL 1
+typedef struct kllm_comm kllm_comm;
+int kllm_comm_unique_id(unsigned char* out128);
+/* max_count: largest vector (floats, multiple of 4) ever reduced = the model dim. */
+int kllm_comm_create(int world, int rank, int backend, int max_count, const unsigned char* nccl_id128,
+                     kllm_comm** out);
+int kllm_comm_ipc_handle(kllm_comm* comm, unsigned char* out64);
+/* handles: world x 64 bytes, rank-ordered (own entry ignored).  Every rank must have connected
+ * (caller barrier) before the first all-reduce, and must stop reducing before any rank destroys. */
+int kllm_comm_connect(kllm_comm* comm, const unsigned char* handles);
+/* out = (residual ? residual : 0) + sum over ranks of `partial`, summed in rank order; all
+ * device pointers, 16-byte aligned, count a multiple of 4.  `partial` is clobbered (NCCL). */
+int kllm_comm_allreduce_residual(kllm_comm* comm, const float* partial, const float* residual, float* out,
+                                 int count, void* stream);
+/* In-place sum; signature of kllm_decoder_desc.allreduce (ctx = the kllm_comm). */
+int kllm_comm_allreduce(void* comm, float* buf, int count, void* stream);
+int kllm_comm_info(const kllm_comm* comm, int* world, int* rank, int* backend);
+void kllm_comm_destroy(kllm_comm* comm);
+
 /* ---- whole decoder ------------------------------------------------------------------------
  * Device-resident model: replaces Model::{init_mem,forward,predict,post_processing,embedding,
  * fill_input} (llama3.cpp:425-500,147-167,642-650,733-745,578-598; model.cpp:245-263) for the
@@ -159,6 +189,9 @@ typedef struct {
   int32_t tp_size, tp_rank;
   int (*allreduce)(void* ctx, float* buf, int count, void* stream);
   void* allreduce_ctx;
+  /* preferred over the callback when set: the decoder then uses the fused
+   * all-reduce + residual add of kllm_comm_allreduce_residual */
+  kllm_comm* comm;
 } kllm_decoder_desc;
 
 typedef struct kllm_decoder kllm_decoder;

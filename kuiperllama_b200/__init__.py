@@ -57,7 +57,7 @@ class DecoderDesc(ctypes.Structure):
         ("s3", POINTER(c_void_p)), ("scls", c_void_p),
         ("bq", POINTER(c_void_p)), ("bk", POINTER(c_void_p)), ("bv", POINTER(c_void_p)),
         ("tp_size", c_int32), ("tp_rank", c_int32),
-        ("allreduce", ALLREDUCE_FN), ("allreduce_ctx", c_void_p),
+        ("allreduce", ALLREDUCE_FN), ("allreduce_ctx", c_void_p), ("comm", c_void_p),
     ]
 
 
@@ -81,6 +81,14 @@ _SIGNATURES = {
     "kllm_argmax_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     "kllm_argmax_f32_sync": (c_int64, [c_void_p, c_int64, c_void_p]),
     "kllm_gemv_fused": (c_int, [POINTER(GemvJob), c_void_p]),
+    "kllm_comm_unique_id": (c_int, [c_void_p]),
+    "kllm_comm_create": (c_int, [c_int, c_int, c_int, c_int, c_void_p, POINTER(c_void_p)]),
+    "kllm_comm_ipc_handle": (c_int, [c_void_p, c_void_p]),
+    "kllm_comm_connect": (c_int, [c_void_p, c_void_p]),
+    "kllm_comm_allreduce_residual": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "kllm_comm_allreduce": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "kllm_comm_info": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "kllm_comm_destroy": (None, [c_void_p]),
     "kllm_decoder_create": (c_int, [POINTER(DecoderDesc), c_void_p, POINTER(c_void_p)]),
     "kllm_decoder_destroy": (None, [c_void_p]),
     "kllm_decoder_step": (c_int, [c_void_p, c_int32, c_int32, c_int, POINTER(c_int32)]),

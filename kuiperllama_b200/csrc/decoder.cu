@@ -141,6 +141,14 @@ std::vector<T> copy_ptrs(const T* src, int n) {
   return v;
 }
 
+// x += all-reduce(tp_tmp): the row-parallel matmul's partial sums meet here
+int tp_reduce_into_x(kllm_decoder* dc, cudaStream_t s) {
+  const kllm_decoder_desc& d = dc->d;
+  if (d.comm != nullptr) return kllm_comm_allreduce_residual(d.comm, dc->tp_tmp, dc->x, dc->x, d.dim, s);
+  KLLM_TRY(d.allreduce(d.allreduce_ctx, dc->tp_tmp, d.dim, s));
+  return kllm_add_f32(dc->x, dc->tp_tmp, dc->x, d.dim, s);
+}
+
 int enqueue_step(kllm_decoder* dc, bool with_teacher, cudaStream_t s) {
   const kllm_decoder_desc& d = dc->d;
   const int dim = d.dim, L = d.layer_num, hid = d.hidden_dim;
@@ -192,10 +200,7 @@ int enqueue_step(kllm_decoder* dc, bool with_teacher, cudaStream_t s) {
       j.seg[0] = {dc->wo[l], d.group_size ? dc->so[l] : nullptr, nullptr, tp ? dc->tp_tmp : dc->x, dim};
       j.residual = tp ? nullptr : dc->x;  // feed_forward's first add (llama3.cpp:683-684)
       KLLM_TRY(gemv_dispatch(&j, GemvExtra{}, s));
-      if (tp) {
-        KLLM_TRY(d.allreduce(d.allreduce_ctx, dc->tp_tmp, dim, s));
-        KLLM_TRY(kllm_add_f32(dc->x, dc->tp_tmp, dc->x, dim, s));
-      }
+      if (tp) KLLM_TRY(tp_reduce_into_x(dc, s));
     }
     // feed_forward (llama3.cpp:686-720)
     {
@@ -220,10 +225,7 @@ int enqueue_step(kllm_decoder* dc, bool with_teacher, cudaStream_t s) {
       j.seg[0] = {dc->w2[l], d.group_size ? dc->s2[l] : nullptr, nullptr, tp ? dc->tp_tmp : dc->x, dim};
       j.residual = tp ? nullptr : dc->x;
       KLLM_TRY(gemv_dispatch(&j, GemvExtra{}, s));
-      if (tp) {
-        KLLM_TRY(d.allreduce(d.allreduce_ctx, dc->tp_tmp, dim, s));
-        KLLM_TRY(kllm_add_f32(dc->x, dc->tp_tmp, dc->x, dim, s));
-      }
+      if (tp) KLLM_TRY(tp_reduce_into_x(dc, s));
     }
   }
   // cls_logits (llama3.cpp:722-731) + post_processing (:733-745)
@@ -279,7 +281,7 @@ int kllm_decoder_create(const kllm_decoder_desc* desc, void* stream, kllm_decode
   if (d.group_size > 0 && (!d.sq || !d.sk || !d.sv || !d.so || !d.s1 || !d.s2 || !d.s3 || !d.scls))
     return KLLM_E_INVALID;
   const int tp = d.tp_size > 1 ? d.tp_size : 1;
-  if (tp > 1 && d.allreduce == nullptr) return KLLM_E_INVALID;
+  if (tp > 1 && d.allreduce == nullptr && d.comm == nullptr) return KLLM_E_INVALID;
   // head_size from the FULL model: dim / (head_num * tp)
   if (d.dim % (d.head_num * tp) != 0 || d.head_num % d.kv_head_num != 0) return KLLM_E_INVALID;
   if ((d.dim & 3) != 0 || (d.hidden_dim & 3) != 0) return KLLM_E_UNSUPPORTED;

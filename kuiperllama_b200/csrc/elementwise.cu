@@ -266,6 +266,7 @@ const char* kllm_error_string(int code) {
     case KLLM_E_UNSUPPORTED: return "unsupported shape";
     case KLLM_E_STATE: return "invalid decoder state";
     case KLLM_E_NODEVICE: return "no CUDA device";
+    case KLLM_E_COMM: return "tensor-parallel transport unavailable or failed";
     default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown";
   }
 }

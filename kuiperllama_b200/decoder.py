@@ -73,6 +73,8 @@ SHAPES = {
     "small-hs48": ModelShape("small-hs48-fp32", 288, 768, 3, 6, 6, 4096, 160),
     "small-int8": ModelShape("small-int8", 256, 768, 2, 4, 2, 1024, 96, group_size=64),
     "small-qwen": ModelShape("small-qwen2", 256, 704, 2, 4, 2, 1536, 128, True, flavour="qwen2"),
+    # 8 heads / 2 kv heads: splits 2 ways (kv heads sharded) and 4 ways (kv heads replicated)
+    "small-tp": ModelShape("small-tp-fp32", 256, 768, 3, 8, 2, 2048, 128),
 }
 
 
@@ -139,7 +141,7 @@ class Decoder:
     """Owns a ``kllm_decoder`` built over torch-held device weights."""
 
     def __init__(self, shape: ModelShape, weights: dict, stream=None, tp_size=1, tp_rank=0,
-                 allreduce=None, allreduce_ctx=None, full_dim=None):
+                 allreduce=None, allreduce_ctx=None, full_dim=None, comm=None):
         self.lib = load_library()
         self.shape = shape
         self.weights = weights  # keep the tensors alive
@@ -176,7 +178,13 @@ class Decoder:
         if allreduce is not None:
             d.allreduce = allreduce
             d.allreduce_ctx = allreduce_ctx
+        if comm is not None:
+            d.comm = comm.handle
+            self.comm = comm  # keep alive
         self.desc = d
+        # local head geometry (head counts in `shape` are per-rank under tensor parallelism)
+        self.head_size = d.dim // (s.head_num * max(tp_size, 1))
+        self.local_kv_dim = s.kv_head_num * self.head_size
         handle = ctypes.c_void_p()
         stream_ptr = ctypes.c_void_p(stream) if stream else None
         check(self.lib.kllm_decoder_create(ctypes.byref(d), stream_ptr, ctypes.byref(handle)),
@@ -229,7 +237,7 @@ class Decoder:
         """(key, value) caches as numpy arrays [L, seq_len, kv_dim] in the reference layout."""
         import numpy as np
         s = self.shape
-        k = np.empty((s.layer_num, s.seq_len, s.kv_dim), np.float32)
+        k = np.empty((s.layer_num, s.seq_len, self.local_kv_dim), np.float32)
         v = np.empty_like(k)
         check(self.lib.kllm_decoder_read_kv(self.handle, k.ctypes.data_as(ctypes.c_void_p),
                                             v.ctypes.data_as(ctypes.c_void_p)), "kllm_decoder_read_kv")
