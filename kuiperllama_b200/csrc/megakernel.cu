@@ -39,7 +39,7 @@ namespace mega {
 
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kThreads = kConsumerThreads + 32;  // + one producer warp
+constexpr int kThreads = kConsumerThreads + 64;  // + the ring producer warp + the L2 prefetch warp
 constexpr int kMaxStages = 16;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -77,6 +77,10 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
+}
+// Non-blocking "pull this span into L2": no shared memory, no completion to wait for.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint64_t policy_evict_last() {
   uint64_t p;
@@ -433,6 +437,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
   // here (they are usually in different phases).
   __shared__ Phase s_phase_cons;
   __shared__ Phase s_phase_prod;
+  __shared__ Phase s_phase_pf;
+  __shared__ volatile unsigned s_fill_count;  // ring stages the producer has issued so far
 
   float* xs = reinterpret_cast<float*>(smem);
   unsigned char* stages = smem + P.xbuf_bytes;
@@ -445,6 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
   const int G = gridDim.x;
 
   if (tid == 0) {
+    s_fill_count = 0u;
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kConsumerWarps);
@@ -460,6 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
   if (is_producer) {
     const uint64_t policy = policy_evict_first();  // weights: streamed once per token
     const uint64_t policy_kv = policy_evict_last();  // KV tiles: re-read every token, keep in L2
+    unsigned filled = 0u;
     int ppos = P.state->pos;
     for (int tok = 0; tok < P.n_tokens; ++tok, ++ppos) {
       for (int pi = 0; pi < P.n_phases; ++pi) {
@@ -512,6 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
                          &full_bar[pipe.slot], policy_kv);
               }
               pipe.advance(S);
+              if (lane == 0) s_fill_count = ++filled; else ++filled;
             }
           }
           continue;
@@ -545,6 +554,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
               }
             }
             pipe.advance(S);
+            if (lane == 0) s_fill_count = ++filled; else ++filled;
           }
         } else {
           for (int u = u0; u < u1; ++u) {
@@ -563,10 +573,77 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
               }
               __syncwarp();
               pipe.advance(S);
+              if (lane == 0) s_fill_count = ++filled; else ++filled;
             }
           }
         }
         
+      }
+    }
+    return;
+  }
+
+  // =============================== L2 prefetch warp ==============================================
+  // The ring (num_stages x stage_bytes per SM, ~4 us of HBM time chip-wide) is shallower than the
+  // dead time around a grid barrier or an attention phase, so HBM would idle there.  This warp
+  // walks the same weight schedule as the producer, pf_stages ring-stages AHEAD of it, and only
+  // pulls the bytes into L2 (cp.async.bulk.prefetch.L2): the outstanding window keeps HBM
+  // streaming while the SMs wait for each other, and the ring then refills from L2.
+  if (warp == kConsumerWarps + 1) {
+    if (P.pf_stages <= 0) return;
+    unsigned ahead = 0u;  // stages walked by this warp (same counting as the producer's `filled`)
+    int ppos = P.state->pos;
+    for (int tok = 0; tok < P.n_tokens; ++tok, ++ppos) {
+      for (int pi = 0; pi < P.n_phases; ++pi) {
+        {
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(P.phases + pi);
+          uint32_t* dst = reinterpret_cast<uint32_t*>(&s_phase_pf);
+          __syncwarp();
+          for (int i = lane; i < static_cast<int>(sizeof(Phase) / 4); i += 32) dst[i] = __ldg(src + i);
+          __syncwarp();
+        }
+        const Phase& ph = s_phase_pf;
+        if (ph.kind == kPhaseAttention) {  // KV tiles are L2-resident already (evict_last): count only
+          if (cta < P.head_num && ppos > 0) ahead += 2u * static_cast<unsigned>(attn_tiles(ppos, P.attn_tile));
+          continue;
+        }
+        const int u0 = static_cast<int>(static_cast<long long>(cta) * ph.units / G);
+        const int u1 = static_cast<int>(static_cast<long long>(cta + 1) * ph.units / G);
+        const int rpu = ph.swiglu ? 2 : 1;
+        const int row_bytes = ph.in_dim * wbytes;
+        auto throttle = [&]() {
+          while (static_cast<int>(ahead - s_fill_count) >= P.pf_stages) __nanosleep(64);
+        };
+        if (ph.chunks_per_row == 1) {
+          const int ups = ph.rows_per_stage / rpu;
+          for (int u = u0; u < u1; u += ups) {
+            const int nrows = min(ups, u1 - u) * rpu;
+            throttle();
+            for (int i = lane; i < nrows; i += 32) {
+              const RowRef rr = resolve_row(ph, u + i / rpu, i % rpu);
+              const long long e = static_cast<long long>(rr.row) * ph.in_dim;
+              bulk_prefetch_l2(static_cast<const unsigned char*>(ph.seg[rr.seg].w) + e * wbytes, row_bytes);
+              if (ph.scale_row_bytes) {
+                const long long g0 = ph.group_shift >= 0 ? (e >> ph.group_shift) : (e / ph.group_size);
+                bulk_prefetch_l2(ph.seg[rr.seg].scales + g0, ph.scale_row_bytes);
+              }
+            }
+            ++ahead;
+          }
+        } else {
+          for (int u = u0; u < u1; ++u) {
+            const RowRef rr = resolve_row(ph, u, 0);
+            const unsigned char* src = static_cast<const unsigned char*>(ph.seg[rr.seg].w) +
+                                       static_cast<long long>(rr.row) * row_bytes;
+            for (int c = 0; c < ph.chunks_per_row; ++c) {
+              const int e0 = c * ph.chunk_elems;
+              const int ne = min(ph.chunk_elems, ph.in_dim - e0);
+              throttle();
+              if (lane == 0) bulk_prefetch_l2(src + static_cast<size_t>(e0) * wbytes, static_cast<uint32_t>(ne) * wbytes);
+              ++ahead;
+            }
+          }
+        }
       }
     }
     return;
@@ -1080,6 +1157,8 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
   P.stage_bytes = stage_bytes_;
   P.xbuf_bytes = xbuf_bytes_;
   P.attn_tile = attn_tile_;
+  P.pf_stages = 8;  // 8 x 32 KB x 148 SMs = 38 MB of weights in flight towards L2 (measured: 6-12 best, >=24 thrashes L2)
+  if (const char* e = getenv("KLLM_PREFETCH_STAGES")) P.pf_stages = std::max(0, atoi(e));
   P.group_size = m.group_size;
   P.dim = m.dim;
   P.vocab_size = m.vocab_size;

@@ -54,6 +54,7 @@ struct Params {
   int n_phases, n_tokens;
   int num_stages, stage_bytes, xbuf_bytes;
   int attn_tile;  // timesteps per K/V ring stage
+  int pf_stages;  // L2 prefetch run-ahead of the ring producer, in ring stages (0 = off)
   int group_size;
   int dim, vocab_size, head_num, head_size, kv_dim, kv_mul, seq_len, flavour;
   const float* tok_emb;

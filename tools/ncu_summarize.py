@@ -56,5 +56,30 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def traffic(src, dst, workload, key, units_per_launch, note=""):
+    """Append/replace profiles/dominant_kernel_traffic.json[workload][key] from an ncu --set full
+    capture: dram__bytes_read.sum + dram__bytes_write.sum of the FIRST kernel in the report,
+    divided by the units (tokens) that launch processed."""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, r = rows[0], rows[1], rows[2]
+
+    def val(name):
+        i = hdr.index(name)
+        v = float(r[i].replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(units[i], 1)
+    rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    n = float(units_per_launch)
+    db = json.load(open(dst)) if os.path.exists(dst) else {}
+    db.setdefault(workload, {})[key] = {
+        "dram_bytes_per_token": (rd + wr) / n, "dram_read_bytes_per_launch": rd, "dram_write_bytes_per_launch": wr,
+        "tokens_per_launch": n, "kernel": r[hdr.index("Kernel Name")][:60], "source": os.path.basename(src),
+        "note": note}
+    json.dump(db, open(dst, "w"), indent=1)
+    print(json.dumps(db[workload][key], indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](*sys.argv[2:])
