@@ -236,6 +236,15 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def _leave_process_group():
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 def run_ours(args, rank, world):
     import torch
     from kuiperllama_b200 import SHAPES, Decoder, load_library, synth_weights
@@ -314,8 +323,13 @@ def run_ours(args, rank, world):
     if rank != 0:
         dec.close()
         if comm:
-            comm.close()
+            comm.close()  # collective (barrier): rank 0 does the same right below
+        _leave_process_group()
         return
+    if comm:
+        dec_engine, dec_launches = dec.engine, dec.launches_per_step
+        dec.close()
+        comm.close()
 
     tok_s = K / (ms / 1e3)
     bytes_tok = shape.weight_bytes_per_token()
@@ -335,7 +349,7 @@ def run_ours(args, rank, world):
                    "parallelism": "single GPU" if world == 1 else f"tp{world}",
                    "l2": "no flush: every step streams %.2f GB of weights >> 126 MB L2" % (bytes_tok / 1e9),
                    "weight_bytes_per_token": bytes_tok,
-                   "launches_per_step": dec.launches_per_step},
+                   "launches_per_step": dec_launches if comm else dec.launches_per_step},
         "e2e": {"value": K / (ms_e2e / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": 16,
                 "d2h_bytes_per_step": 16},
         "gpu_launches": int(launches),
@@ -344,7 +358,7 @@ def run_ours(args, rank, world):
     if world > 1:
         line["config"]["tp_comm"] = comm.backend
         line["config"]["weight_bytes_per_token_per_gpu"] = bytes_tok_gpu
-    engine = dec.engine
+    engine = dec_engine if comm else dec.engine
     line["config"]["engine"] = engine
     algo, sec, n = dominant_kernel_roofline(lib, local, w, stream_ptr, torch)
     gemv = {"bound": "hbm", "achieved": algo / sec / 1e9, "peak": peak, "unit": "GB/s",
@@ -375,6 +389,8 @@ def run_ours(args, rank, world):
         line["cpu_baseline"] = cpu_baseline(shape, w, args.cpu_seconds)
     print(json.dumps(line))
     sys.stdout.flush()
+    if world > 1:
+        _leave_process_group()
 
 
 def main():

@@ -352,8 +352,19 @@ int kllm_decoder_create(const kllm_decoder_desc* desc, void* stream, kllm_decode
   const char* want = getenv("KLLM_ENGINE");
   const bool force_graph = want != nullptr && strcmp(want, "graph") == 0;
   const bool force_mega = want != nullptr && strcmp(want, "persistent") == 0;
-  if (!force_graph && tp == 1) {
+  // tensor parallel: the persistent engine needs the peer-memory transport (its exchange IS
+  // the all-reduce); with NCCL or a caller-supplied callback the graph engine is used
+  unsigned long long* tp_areas[8] = {};
+  int tp_world = 1, tp_rank = 0, tp_stride = 0;
+  bool mega_ok = tp == 1;
+  if (tp > 1 && d.comm != nullptr &&
+      comm_tagged_areas(d.comm, tp_areas, &tp_world, &tp_rank, &tp_stride) == 0 && tp_world == tp &&
+      tp_stride >= d.dim)
+    mega_ok = true;
+  if (!force_graph && mega_ok) {
     MegaModel mm{};
+    mm.tp_world = tp, mm.tp_rank = tp_rank, mm.tp_stride = tp_stride;
+    for (int r = 0; r < 8; ++r) mm.tp_data[r] = tp_areas[r];
     mm.dim = d.dim, mm.hidden_dim = d.hidden_dim, mm.layer_num = L, mm.head_num = d.head_num;
     mm.kv_head_num = d.kv_head_num, mm.vocab_size = d.vocab_size, mm.seq_len = d.seq_len;
     mm.head_size = dc->head_size, mm.kv_dim = dc->kv_dim, mm.kv_mul = dc->kv_mul;

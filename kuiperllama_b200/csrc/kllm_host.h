@@ -35,5 +35,8 @@ int launch_mha(PosArg pos, int head_num, int layer_index, int seq_len, int kv_di
                int head_size, float* mha_out, const float* query, float* score,
                const float* key_cache, const float* value_cache, cudaStream_t stream);
 
+// tp_comm.cu: exchange areas [2][world][stride] of 64-bit tagged words, one per rank (peer transport)
+int comm_tagged_areas(kllm_comm* comm, unsigned long long** areas8, int* world, int* rank, int* stride);
+
 inline float flavour_eps(int flavour) { return flavour == KLLM_FLAVOUR_QWEN2 ? 1e-6f : 1e-5f; }
 }  // namespace kllm

@@ -95,6 +95,16 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// 64-bit {tag, value} words of the tagged exchange: single-copy atomic, so value and tag travel
+// together and no fence or flag is needed between a writer on one GPU and a reader on another.
+__device__ __forceinline__ void st_tagged(unsigned long long* p, float v, unsigned tag) {
+  const unsigned long long w = (static_cast<unsigned long long>(tag) << 32) | __float_as_uint(v);
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ void ld_tagged2(const unsigned long long* p, unsigned long long& a,
+                                           unsigned long long& b) {
+  asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
 __device__ __forceinline__ void consumer_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
 }
@@ -489,7 +499,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
           // reads after the grid barrier that closed the previous token's attention phase.
           if (tok > 0 && lane == 0) {
             const unsigned need = P.barrier_base +
-                                  static_cast<unsigned>((tok - 1) * P.n_phases + pi + 1) * static_cast<unsigned>(G);
+                                  static_cast<unsigned>((tok - 1) * P.bars_per_token + ph.barrier_idx) *
+                                      static_cast<unsigned>(G);
             while (static_cast<int>(ld_acquire_u32(P.barrier) - need) < 0) {
             }
             asm volatile("fence.proxy.async;" ::: "memory");
@@ -661,11 +672,15 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
     ArgBest best{0.f, -1};
 
     const bool prof_on = P.prof != nullptr && tok == P.prof_token && tid == 0;
+    bool prev_barrier = true;
     for (int pi = 0; pi < P.n_phases; ++pi) {
       {
-        // (the grid barrier that ended the previous phase is the hazard fence for this copy)
+        // the grid barrier that ended the previous phase is the hazard fence for this copy; a
+        // phase closed by a tagged exchange has none, so fence the CTA's own warps here
+        if (!prev_barrier) consumer_sync();
         const uint32_t* src = reinterpret_cast<const uint32_t*>(P.phases + pi);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&s_phase_cons);
+        static_assert(sizeof(Phase) / 4 <= kConsumerThreads, "phase copy");
         if (tid < static_cast<int>(sizeof(Phase) / 4)) dst[tid] = __ldg(src + tid);
         consumer_sync();
       }
@@ -679,12 +694,82 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
           attention_phase(P, ph, cta, pos, xs, s_warp, &s_bcast, stages, full_bar, empty_bar, pipe);
         if (stamp) stamp[1] = stamp[2] = global_ns();
         grid_barrier(P.barrier, bar_target, G);
+        prev_barrier = true;
         if (stamp) stamp[3] = global_ns();
         continue;
       }
+      prev_barrier = ph.barrier_after != 0;
 
       // ---- stage the input vector (and RMS-normalise it) --------------------------------------
       const int M = ph.in_dim;
+      if (ph.tp_in) {
+        // x = x_old + (p_0 + ... + p_{W-1}); the partials arrive as tagged words from every rank
+        // (this one included) and are polled in place: no grid barrier, no all-reduce kernel.
+        const unsigned tag = P.tp_seq_base + static_cast<unsigned>(tok * P.exch_per_token + ph.exch) + 1u;
+        const int W = P.tp_world;
+        const unsigned long long* area =
+            P.tp_data[P.tp_rank] + static_cast<size_t>(tag & 1u) * W * P.tp_stride;
+        const float* xo = ph.x_old != nullptr ? ph.x_old : emb_row;
+        const int s0 = static_cast<int>(static_cast<long long>(cta) * M / G);
+        const int s1 = static_cast<int>(static_cast<long long>(cta + 1) * M / G);
+        const int pairs = M >> 1;
+        const long long t_start = clock64();
+        for (int base = 0; base < pairs; base += 4 * kConsumerThreads) {
+          float acc[4][2];
+          float xold[4][2];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int pr = base + k * kConsumerThreads + tid;
+            if (pr < pairs) {
+              const float2 v = __ldcg(reinterpret_cast<const float2*>(xo) + pr);
+              xold[k][0] = v.x, xold[k][1] = v.y;
+            }
+          }
+          for (int r = 0; r < W; ++r) {
+            const unsigned long long* row = area + static_cast<size_t>(r) * P.tp_stride;
+            unsigned long long w[4][2];
+            bool ok;
+            do {
+              ok = true;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int pr = base + k * kConsumerThreads + tid;
+                if (pr < pairs) ld_tagged2(row + 2 * pr, w[k][0], w[k][1]);
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int pr = base + k * kConsumerThreads + tid;
+                if (pr < pairs)
+                  ok = ok && static_cast<unsigned>(w[k][0] >> 32) == tag && static_cast<unsigned>(w[k][1] >> 32) == tag;
+              }
+              if (!ok && clock64() - t_start > 8000000000LL) {
+                printf("kllm mega: rank %d cta %d timed out on exchange tag %u from rank %d\n", P.tp_rank, cta, tag, r);
+                __trap();
+              }
+            } while (!ok);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              if (base + k * kConsumerThreads + tid >= pairs) continue;
+              const float a = __uint_as_float(static_cast<unsigned>(w[k][0]));
+              const float b = __uint_as_float(static_cast<unsigned>(w[k][1]));
+              acc[k][0] = r == 0 ? a : __fadd_rn(acc[k][0], a);
+              acc[k][1] = r == 0 ? b : __fadd_rn(acc[k][1], b);
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int pr = base + k * kConsumerThreads + tid;
+            if (pr < pairs) {
+              const float x0 = __fadd_rn(xold[k][0], acc[k][0]);  // llama3.cpp:683,719: x + out
+              const float x1 = __fadd_rn(xold[k][1], acc[k][1]);
+              xs[2 * pr] = x0, xs[2 * pr + 1] = x1;
+              if (2 * pr >= s0 && 2 * pr < s1) ph.x_new[2 * pr] = x0;
+              if (2 * pr + 1 >= s0 && 2 * pr + 1 < s1) ph.x_new[2 * pr + 1] = x1;
+            }
+          }
+        }
+        consumer_sync();
+      }
       {
         const float* xg = ph.x_from_emb ? emb_row : ph.x;
         const float4* xg4 = reinterpret_cast<const float4*>(xg);
@@ -702,8 +787,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
             if (i < n4) nw[k] = __ldg(nw4 + i);
           }
         }
-        for (int i = tid; i < n4; i += kConsumerThreads) xs4w[i] = __ldcg(xg4 + i);
-        consumer_sync();
+        if (!ph.tp_in) {
+          for (int i = tid; i < n4; i += kConsumerThreads) xs4w[i] = __ldcg(xg4 + i);
+          consumer_sync();
+        }
         if (ph.norm_w != nullptr) {
           if (warp == 0) {
             const float sc = rms_scale_smem(xs, M, ph.norm_eps, lane);
@@ -754,6 +841,12 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
         // lane 0 only
         if (ph.swiglu) {
           ph.seg[0].out[unit] = swiglu_ref(d0, d1);
+          return;
+        }
+        if (ph.tp_out) {
+          const unsigned tag = P.tp_seq_base + static_cast<unsigned>(tok * P.exch_per_token + ph.exch) + 1u;
+          const size_t off = (static_cast<size_t>(tag & 1u) * P.tp_world + P.tp_rank) * P.tp_stride + unit;
+          for (int k = 1; k <= P.tp_world; ++k) st_tagged(P.tp_data[(P.tp_rank + k) % P.tp_world] + off, d0, tag);
           return;
         }
         const RowRef rr = resolve_row(ph, unit, 0);
@@ -900,7 +993,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
         stamp[7] = static_cast<unsigned long long>(cyc4[3]);
         (void)cyc_wait, (void)cyc_rows;
       }
-      grid_barrier(P.barrier, bar_target, G);
+      if (ph.barrier_after) grid_barrier(P.barrier, bar_target, G);
       if (stamp) stamp[3] = global_ns();
     }
 
@@ -1026,6 +1119,55 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
     return 0;
   };
 
+  // Tagged exchange instead of "write x, grid barrier, read x" after o_proj and down_proj:
+  // mandatory under tensor parallelism (it IS the all-reduce), optional on one GPU.
+  const int W = m.tp_world > 1 ? m.tp_world : 1;
+  tagged_ = W > 1;
+  if (const char* e = getenv("KLLM_MEGA_TAGGED")) tagged_ = tagged_ || atoi(e) != 0;
+  else tagged_ = true;
+  if (tagged_) {
+    if (cudaMalloc(&d_xbuf_, sizeof(float) * 2 * dim) != cudaSuccess) return static_cast<int>(cudaErrorMemoryAllocation);
+    cudaMemsetAsync(d_xbuf_, 0, sizeof(float) * 2 * dim, stream);
+    if (W == 1) {
+      if (cudaMalloc(&d_tagged_, sizeof(unsigned long long) * 2 * dim) != cudaSuccess)
+        return static_cast<int>(cudaErrorMemoryAllocation);
+      cudaMemsetAsync(d_tagged_, 0, sizeof(unsigned long long) * 2 * dim, stream);
+    }
+  }
+  auto xbuf_of = [&](int e) { return d_xbuf_ + static_cast<size_t>(e & 1) * dim; };
+  int exch = 0, bars = 0;
+  auto close_phase = [&](Phase& p, bool barrier) {
+    p.barrier_after = barrier ? 1 : 0;
+    if (barrier) ++bars;
+    p.barrier_idx = bars;
+  };
+  // a phase whose input is the residual stream: tagged -> x_old + partials of the last exchange
+  auto input_is_x = [&](Phase& p) {
+    if (!tagged_ || exch == 0) {
+      p.x = m.x;
+      return;
+    }
+    p.tp_in = 1;
+    p.exch = exch - 1;
+    p.x_old = exch >= 2 ? xbuf_of(exch - 2) : nullptr;  // nullptr: the embedding row
+    p.x_new = xbuf_of(exch - 1);
+    p.x = nullptr;
+  };
+  // a row-parallel matmul whose output is added to the residual stream
+  auto output_adds_to_x = [&](Phase& p, bool first_layer) {
+    if (tagged_) {
+      p.tp_out = 1;
+      p.exch = exch++;
+      p.residual = nullptr;
+      p.residual_from_emb = 0;
+      close_phase(p, false);
+    } else {
+      p.residual = m.x;
+      p.residual_from_emb = first_layer ? 1 : 0;
+      close_phase(p, true);
+    }
+  };
+
   const float eps = flavour_eps(m.flavour);
   for (int l = 0; l < m.layer_num; ++l) {
     const size_t layer_off = static_cast<size_t>(l) * m.seq_len * kvd;
@@ -1034,7 +1176,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       p.kind = mega::kPhaseGemv;
       p.in_dim = dim;
       p.n_seg = 3;
-      p.x = m.x;
+      input_is_x(p);
       p.x_from_emb = (l == 0);
       p.norm_w = m.attn_norm[l];
       p.norm_eps = eps;
@@ -1044,12 +1186,14 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
                   m.value_cache + layer_off, 0, kvd, 1};
       p.units = q_rows + 2 * kvd;
       if (int rc = plan(p)) return rc;
+      close_phase(p, true);
       ph.push_back(p);
     }
     {
       Phase p{};
       p.kind = mega::kPhaseAttention;
       p.layer = l;
+      close_phase(p, true);
       ph.push_back(p);
     }
     {  // wo + residual (llama3.cpp:672-684)
@@ -1059,10 +1203,9 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       p.n_seg = 1;
       p.x = m.attn_out;
       p.seg[0] = {m.wo[l], int8 ? m.so[l] : nullptr, nullptr, m.x, 0, dim, 0};
-      p.residual = m.x;
-      p.residual_from_emb = (l == 0);
       p.units = dim;
       if (int rc = plan(p)) return rc;
+      output_adds_to_x(p, l == 0);
       ph.push_back(p);
     }
     {  // ffn rmsnorm + w1 | w3 -> swiglu (llama3.cpp:686-708)
@@ -1071,13 +1214,14 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       p.in_dim = dim;
       p.n_seg = 2;
       p.swiglu = 1;
-      p.x = m.x;
+      input_is_x(p);
       p.norm_w = m.ffn_norm[l];
       p.norm_eps = eps;
       p.seg[0] = {m.w1[l], int8 ? m.s1[l] : nullptr, nullptr, m.h, 0, hid, 0};
       p.seg[1] = {m.w3[l], int8 ? m.s3[l] : nullptr, nullptr, nullptr, 0, hid, 0};
       p.units = hid;
       if (int rc = plan(p)) return rc;
+      close_phase(p, true);
       ph.push_back(p);
     }
     {  // w2 + residual (llama3.cpp:711-719)
@@ -1087,9 +1231,9 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       p.n_seg = 1;
       p.x = m.h;
       p.seg[0] = {m.w2[l], int8 ? m.s2[l] : nullptr, nullptr, m.x, 0, dim, 0};
-      p.residual = m.x;
       p.units = dim;
       if (int rc = plan(p)) return rc;
+      output_adds_to_x(p, false);
       ph.push_back(p);
     }
   }
@@ -1098,17 +1242,19 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
     p.kind = mega::kPhaseGemv;
     p.in_dim = dim;
     p.n_seg = 1;
-    p.x = m.x;
+    input_is_x(p);
     p.norm_w = m.final_norm;
     p.norm_eps = eps;
     p.seg[0] = {m.wcls, int8 ? m.scls : nullptr, nullptr, m.logits, 0, m.vocab_size, 0};
     p.units = m.vocab_size;
     p.argmax = 1;
     if (int rc = plan(p)) return rc;
+    close_phase(p, true);
     ph.push_back(p);
   }
   n_phases_ = static_cast<int>(ph.size());
-  n_barriers_per_token_ = n_phases_;
+  n_barriers_per_token_ = bars;
+  exch_per_token_ = exch;
 
   if (cudaMalloc(&d_phases_, sizeof(Phase) * ph.size()) != cudaSuccess) return static_cast<int>(cudaErrorMemoryAllocation);
   cudaMemcpyAsync(d_phases_, ph.data(), sizeof(Phase) * ph.size(), cudaMemcpyHostToDevice, stream);
@@ -1138,6 +1284,10 @@ void MegaEngine::destroy() {
   if (d_barrier_) cudaFree(d_barrier_);
   if (d_arg_val_) cudaFree(d_arg_val_);
   if (d_arg_idx_) cudaFree(d_arg_idx_);
+  if (d_xbuf_) cudaFree(d_xbuf_);
+  if (d_tagged_) cudaFree(d_tagged_);
+  d_xbuf_ = nullptr;
+  d_tagged_ = nullptr;
   d_phases_ = nullptr;
   d_barrier_ = nullptr;
   d_arg_val_ = nullptr;
@@ -1183,6 +1333,14 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
   P.max_steps = m.seq_len;
   P.barrier = static_cast<unsigned*>(d_barrier_);
   P.barrier_base = barrier_base_;
+  P.bars_per_token = n_barriers_per_token_;
+  P.tp_world = m.tp_world > 1 ? m.tp_world : 1;
+  P.tp_rank = m.tp_world > 1 ? m.tp_rank : 0;
+  P.tp_stride = m.tp_world > 1 ? m.tp_stride : m.dim;
+  for (int r = 0; r < 8; ++r) P.tp_data[r] = m.tp_world > 1 ? m.tp_data[r] : nullptr;
+  if (m.tp_world <= 1) P.tp_data[0] = d_tagged_;
+  P.exch_per_token = exch_per_token_;
+  P.tp_seq_base = tp_seq_base_;
   P.arg_val = static_cast<float*>(d_arg_val_);
   P.arg_idx = static_cast<int*>(d_arg_idx_);
   P.prof = prof_dev;
@@ -1192,6 +1350,7 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
                                               dim3(grid_), dim3(mega::kThreads), args, smem_bytes_,
                                               stream_);
   if (e != cudaSuccess) return static_cast<int>(e);
+  tp_seq_base_ += static_cast<unsigned>(n_tokens) * static_cast<unsigned>(exch_per_token_);
   barrier_base_ += static_cast<unsigned>(n_tokens) * static_cast<unsigned>(n_barriers_per_token_) *
                    static_cast<unsigned>(grid_);
   count_launch();

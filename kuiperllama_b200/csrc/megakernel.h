@@ -42,6 +42,17 @@ struct Phase {
   const float* x;         // input vector (global memory)
   const float* norm_w;    // optional RMSNorm weight applied to x
   const float* residual;  // optional residual vector
+  // Tagged exchange (replaces the grid barrier AND, under tensor parallelism, the all-reduce):
+  //   tp_out: each produced row is published as {value, tag} -- one 64-bit store -- into every
+  //           rank's exchange area instead of seg[0].out; no residual add, no barrier after.
+  //   tp_in : the input vector is x_old + (p_0 + p_1 + ... + p_{world-1}), p_r = rank r's tagged
+  //           partials of exchange `exch`, polled until their tag is current; the CTA's slice of
+  //           the result is kept in x_new as the next exchange's x_old.
+  int tp_in, tp_out, exch;
+  int barrier_after;      // 1: a grid barrier closes the phase
+  int barrier_idx;        // barriers of this token passed once this phase is closed
+  const float* x_old;     // tp_in: residual stream before the exchange (nullptr: the embedding row)
+  float* x_new;           // tp_in: residual stream after it
   Seg seg[3];
 };
 
@@ -74,6 +85,12 @@ struct Params {
   int max_steps;
   unsigned* barrier;
   unsigned barrier_base;
+  int bars_per_token;
+  // tagged exchange areas: tp_data[r] = rank r's area [2 slots][tp_world][tp_stride] of 64-bit
+  // {tag:32 | fp32 bits:32}; tp_data[tp_rank] is local memory, the others NVLink peer mappings
+  unsigned long long* tp_data[8];
+  int tp_world, tp_rank, tp_stride, exch_per_token;
+  unsigned tp_seq_base;
   float* arg_val;
   int* arg_idx;
   // optional phase timeline of one token: prof[(cta * n_phases + phase) * 4 + k], k = phase
@@ -106,6 +123,10 @@ struct MegaModel {
   const float* sin_cache; const float* cos_cache;
   void* state;
   int32_t* out_tokens;
+  // tensor parallel (tp_world > 1): exchange areas of every rank (kllm_comm, CUDA IPC)
+  int tp_world, tp_rank;
+  unsigned long long* tp_data[8];
+  int tp_stride;
 };
 
 class MegaEngine {
@@ -129,6 +150,11 @@ class MegaEngine {
   void* d_barrier_ = nullptr;
   void* d_arg_val_ = nullptr;
   void* d_arg_idx_ = nullptr;
+  float* d_xbuf_ = nullptr;                // [2][dim]: the residual stream, alternating per exchange
+  unsigned long long* d_tagged_ = nullptr;  // single-GPU exchange area (tp_world == 1)
+  bool tagged_ = false;
+  int exch_per_token_ = 0;
+  unsigned tp_seq_base_ = 0;
   int grid_ = 0, stages_ = 0, stage_bytes_ = 0, xbuf_bytes_ = 0, n_phases_ = 0, attn_tile_ = 0;
   int n_barriers_per_token_ = 0;
   size_t smem_bytes_ = 0;

@@ -150,6 +150,11 @@ struct kllm_comm {
 
 namespace {
 size_t flag_bytes() { return 2 * kFlagStride * sizeof(uint32_t); }
+size_t data_bytes(const kllm_comm* c) { return sizeof(float) * 2 * static_cast<size_t>(c->world) * c->max_count; }
+// the persistent kernel's tagged exchange area follows the one-shot kernel's slots
+unsigned long long* tagged_of(const kllm_comm* c, void* base) {
+  return reinterpret_cast<unsigned long long*>(static_cast<char*>(base) + flag_bytes() + data_bytes(c));
+}
 void fill_table(kllm_comm* c, int r, void* base) {
   c->table.flags[r] = static_cast<uint32_t*>(base);
   c->table.data[r] = reinterpret_cast<float*>(static_cast<char*>(base) + flag_bytes());
@@ -191,7 +196,7 @@ int kllm_comm_create(int world, int rank, int backend, int max_count, const unsi
     }
     c->connected = true;
   } else {
-    c->local_bytes = flag_bytes() + sizeof(float) * 2 * static_cast<size_t>(world) * max_count;
+    c->local_bytes = flag_bytes() + data_bytes(c) + sizeof(unsigned long long) * 2 * static_cast<size_t>(world) * max_count;
     if (cudaMalloc(&c->local, c->local_bytes) != cudaSuccess || cudaMalloc(&c->seq, sizeof(uint32_t)) != cudaSuccess) {
       kllm_comm_destroy(c);
       return static_cast<int>(cudaErrorMemoryAllocation);
@@ -270,6 +275,21 @@ int kllm_comm_info(const kllm_comm* c, int* world, int* rank, int* backend) {
   if (backend) *backend = c->backend;
   return 0;
 }
+
+}  // extern "C"
+
+namespace kllm {
+// Internal (decoder.cu): the tagged exchange areas of every rank for the persistent kernel.
+int comm_tagged_areas(kllm_comm* c, unsigned long long** areas8, int* world, int* rank, int* stride) {
+  if (!c || c->backend != KLLM_COMM_PEER || !c->connected) return KLLM_E_STATE;
+  for (int r = 0; r < kMaxWorld; ++r) areas8[r] = nullptr;
+  for (int r = 0; r < c->world; ++r) areas8[r] = tagged_of(c, r == c->rank ? c->local : c->remote[r]);
+  *world = c->world, *rank = c->rank, *stride = c->max_count;
+  return 0;
+}
+}  // namespace kllm
+
+extern "C" {
 
 void kllm_comm_destroy(kllm_comm* c) {
   if (!c) return;

@@ -155,7 +155,9 @@ def test_comm_allreduce_matches_rank_ordered_sum(kllm_lib, tmp_path, backend, wo
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
 
 
-def _decoder_rank(rank, world, key, backend, steps, out_dir):
+def _decoder_rank(rank, world, key, backend, engine, steps, out_dir):
+    import os
+    os.environ["KLLM_ENGINE"] = engine
     import torch
     from kuiperllama_b200 import SHAPES, synth_weights
     from kuiperllama_b200.tensor_parallel import Comm, make_tp_decoder
@@ -163,7 +165,7 @@ def _decoder_rank(rank, world, key, backend, steps, out_dir):
     full = synth_weights(shape, "cuda", 11)
     comm = Comm(shape.dim, backend)
     dec = make_tp_decoder(shape, full, comm)
-    assert dec.engine == "graph"
+    assert dec.engine == engine
     ids = dec.generate(1, 0, steps)
     logits = dec.logits()
     # the host-buffer path walks the same sequence
@@ -172,9 +174,14 @@ def _decoder_rank(rank, world, key, backend, steps, out_dir):
         tok = dec.step(tok, pos)
         ids2.append(tok)
     assert ids2 == ids[:8]
-    np.savez(f"{out_dir}/{backend}_rank{rank}.npz", ids=np.array(ids), logits=logits)
+    np.savez(f"{out_dir}/{backend}_{engine}_rank{rank}.npz", ids=np.array(ids), logits=logits)
     dec.close()
     comm.close()
+
+
+# transport x engine: the persistent megakernel exchanges tagged partials over peer memory itself;
+# the graph engine calls the one-shot all-reduce kernel (peer) or ncclAllReduce
+TP_MODES = [("peer", "persistent"), ("peer", "graph"), ("nccl", "graph")]
 
 
 @pytest.mark.gpu
@@ -183,11 +190,10 @@ def test_tp_decoder_matches_unsharded_oracle(kllm_lib, oracle, tmp_path, key, wo
     from kuiperllama_b200.checkpoint import write_checkpoint
     _need_gpus(world)
     steps = 48
-    for backend in ("peer", "nccl"):
-        spawn(_decoder_rank, world, "nccl", (key, backend, steps, str(tmp_path)))
-    shape, w = _full_model(key)   # CPU generator: NOT the weights the GPU ranks drew
-    import torch
-    from kuiperllama_b200 import synth_weights
+    for backend, engine in TP_MODES:
+        spawn(_decoder_rank, world, "nccl", (key, backend, engine, steps, str(tmp_path)))
+    from kuiperllama_b200 import SHAPES, synth_weights
+    shape = SHAPES[key]
     w = synth_weights(shape, "cuda", 11)
     path = tmp_path / "full.bin"
     write_checkpoint(str(path), shape, w)
@@ -197,10 +203,15 @@ def test_tp_decoder_matches_unsharded_oracle(kllm_lib, oracle, tmp_path, key, wo
         tok, logits = om.step(tok, pos)
         want.append(tok)
     om.close()
-    for backend in ("peer", "nccl"):
+    got = {}
+    for backend, engine in TP_MODES:
         for r in range(world):
-            got = np.load(tmp_path / f"{backend}_rank{r}.npz")
-            assert list(got["ids"]) == want, (backend, r)
-            assert np.abs(got["logits"] - logits).max() < TOL
-    a, b = np.load(tmp_path / "peer_rank0.npz")["logits"], np.load(tmp_path / f"peer_rank{world - 1}.npz")["logits"]
-    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+            g = np.load(tmp_path / f"{backend}_{engine}_rank{r}.npz")
+            assert list(g["ids"]) == want, (backend, engine, r)
+            assert np.abs(g["logits"] - logits).max() < TOL
+            got[backend, engine, r] = g["logits"].view(np.uint32)
+    # rank-ordered sums: every rank, and both peer-memory engines, hold identical bits
+    ref = got["peer", "persistent", 0]
+    for r in range(world):
+        assert np.array_equal(got["peer", "persistent", r], ref)
+        assert np.array_equal(got["peer", "graph", r], ref)
