@@ -725,35 +725,51 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
               xold[k][0] = v.x, xold[k][1] = v.y;
             }
           }
-          for (int r = 0; r < W; ++r) {
-            const unsigned long long* row = area + static_cast<size_t>(r) * P.tp_stride;
-            unsigned long long w[4][2];
+          // two ranks per round trip (their loads are all in flight together), summed in rank order
+          for (int r0 = 0; r0 < W; r0 += 2) {
+            const bool two = r0 + 1 < W;
+            const unsigned long long* row0 = area + static_cast<size_t>(r0) * P.tp_stride;
+            const unsigned long long* row1 = row0 + (two ? P.tp_stride : 0);
+            unsigned long long w[2][4][2];
             bool ok;
             do {
               ok = true;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const int pr = base + k * kConsumerThreads + tid;
-                if (pr < pairs) ld_tagged2(row + 2 * pr, w[k][0], w[k][1]);
+                if (pr < pairs) {
+                  ld_tagged2(row0 + 2 * pr, w[0][k][0], w[0][k][1]);
+                  if (two) ld_tagged2(row1 + 2 * pr, w[1][k][0], w[1][k][1]);
+                }
               }
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const int pr = base + k * kConsumerThreads + tid;
-                if (pr < pairs)
-                  ok = ok && static_cast<unsigned>(w[k][0] >> 32) == tag && static_cast<unsigned>(w[k][1] >> 32) == tag;
+                if (pr < pairs) {
+                  ok = ok && static_cast<unsigned>(w[0][k][0] >> 32) == tag &&
+                       static_cast<unsigned>(w[0][k][1] >> 32) == tag;
+                  if (two)
+                    ok = ok && static_cast<unsigned>(w[1][k][0] >> 32) == tag &&
+                         static_cast<unsigned>(w[1][k][1] >> 32) == tag;
+                }
               }
               if (!ok && clock64() - t_start > 8000000000LL) {
-                printf("kllm mega: rank %d cta %d timed out on exchange tag %u from rank %d\n", P.tp_rank, cta, tag, r);
+                printf("kllm mega: rank %d cta %d timed out on exchange tag %u from ranks %d..%d\n", P.tp_rank, cta,
+                       tag, r0, r0 + (two ? 1 : 0));
                 __trap();
               }
             } while (!ok);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               if (base + k * kConsumerThreads + tid >= pairs) continue;
-              const float a = __uint_as_float(static_cast<unsigned>(w[k][0]));
-              const float b = __uint_as_float(static_cast<unsigned>(w[k][1]));
-              acc[k][0] = r == 0 ? a : __fadd_rn(acc[k][0], a);
-              acc[k][1] = r == 0 ? b : __fadd_rn(acc[k][1], b);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                if (j == 1 && !two) continue;
+                const float a = __uint_as_float(static_cast<unsigned>(w[j][k][0]));
+                const float b = __uint_as_float(static_cast<unsigned>(w[j][k][1]));
+                acc[k][0] = (r0 + j) == 0 ? a : __fadd_rn(acc[k][0], a);
+                acc[k][1] = (r0 + j) == 0 ? b : __fadd_rn(acc[k][1], b);
+              }
             }
           }
 #pragma unroll

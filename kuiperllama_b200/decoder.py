@@ -75,6 +75,8 @@ SHAPES = {
     "small-qwen": ModelShape("small-qwen2", 256, 704, 2, 4, 2, 1536, 128, True, flavour="qwen2"),
     # 8 heads / 2 kv heads: splits 2 ways (kv heads sharded) and 4 ways (kv heads replicated)
     "small-tp": ModelShape("small-tp-fp32", 256, 768, 3, 8, 2, 2048, 128),
+    # int8 whose 2-way shards still give the persistent ring 16-byte scale rows
+    "small-tp-int8": ModelShape("small-tp-int8", 512, 1536, 2, 8, 4, 1024, 96, group_size=64),
 }
 
 

@@ -84,7 +84,8 @@ def _gloo_rank(rank, world, key, steps, out_dir):
     np.savez(f"{out_dir}/rank{rank}.npz", ids=np.array(ids), logits=logits)
 
 
-@pytest.mark.parametrize("key,world", [("small-tp", 2), ("small-tp", 4), ("small-int8", 2), ("small-qwen", 2)])
+@pytest.mark.parametrize("key,world", [("small-tp", 2), ("small-tp", 4), ("small-int8", 2), ("small-tp-int8", 2),
+                                       ("small-qwen", 2)])
 def test_gloo_tensor_parallel_decode_matches_unsharded_oracle(oracle, tmp_path, key, world):
     from kuiperllama_b200.checkpoint import write_checkpoint
     steps = 12
@@ -140,7 +141,10 @@ def _comm_rank(rank, world, backend, out_dir):
         for i in range(64):
             comm.allreduce_(got[i], residual=res[i] if i % 2 else None)
         torch.cuda.synchronize()
-        ok = ok and all(bool(torch.equal(a, b)) for a, b in zip(got, want))
+        if backend == "peer" or world == 2:  # rank-ordered by construction (a + b == b + a bitwise)
+            ok = ok and all(bool(torch.equal(a, b)) for a, b in zip(got, want))
+        else:  # NCCL picks its own reduction tree for more than two ranks
+            ok = ok and all(bool(torch.allclose(a, b, rtol=1e-5, atol=1e-5)) for a, b in zip(got, want))
     comm.close()
     assert ok
     open(f"{out_dir}/ok{rank}", "w").write("1")
@@ -148,7 +152,7 @@ def _comm_rank(rank, world, backend, out_dir):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("backend", ["peer", "nccl"])
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4])
 def test_comm_allreduce_matches_rank_ordered_sum(kllm_lib, tmp_path, backend, world):
     _need_gpus(world)
     spawn(_comm_rank, world, "nccl", (backend, str(tmp_path)))
@@ -159,12 +163,20 @@ def _decoder_rank(rank, world, key, backend, engine, steps, out_dir):
     import os
     os.environ["KLLM_ENGINE"] = engine
     import torch
-    from kuiperllama_b200 import SHAPES, synth_weights
+    from kuiperllama_b200 import SHAPES, KllmError, synth_weights
     from kuiperllama_b200.tensor_parallel import Comm, make_tp_decoder
     shape = SHAPES[key]
     full = synth_weights(shape, "cuda", 11)
     comm = Comm(shape.dim, backend)
-    dec = make_tp_decoder(shape, full, comm)
+    try:
+        dec = make_tp_decoder(shape, full, comm)
+    except KllmError as e:
+        # the persistent ring needs 16-byte weight/scale rows; forcing it on a shard it cannot
+        # stage fails loudly (never a silent fallback) -- every rank sees the same refusal
+        assert engine == "persistent" and "unsupported shape" in str(e), e
+        open(f"{out_dir}/{backend}_{engine}_rank{rank}.refused", "w").write(str(e))
+        comm.close()
+        return
     assert dec.engine == engine
     ids = dec.generate(1, 0, steps)
     logits = dec.logits()
@@ -185,7 +197,8 @@ TP_MODES = [("peer", "persistent"), ("peer", "graph"), ("nccl", "graph")]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("key,world", [("small-tp", 2), ("small-int8", 2), ("small-qwen", 2), ("small-tp", 4)])
+@pytest.mark.parametrize("key,world", [("small-tp", 2), ("small-int8", 2), ("small-tp-int8", 2), ("small-qwen", 2),
+                                       ("small-tp", 4)])
 def test_tp_decoder_matches_unsharded_oracle(kllm_lib, oracle, tmp_path, key, world):
     from kuiperllama_b200.checkpoint import write_checkpoint
     _need_gpus(world)
@@ -204,14 +217,19 @@ def test_tp_decoder_matches_unsharded_oracle(kllm_lib, oracle, tmp_path, key, wo
         want.append(tok)
     om.close()
     got = {}
-    for backend, engine in TP_MODES:
+    modes = [m for m in TP_MODES if not (tmp_path / f"{m[0]}_{m[1]}_rank0.refused").exists()]
+    assert ("peer", "graph") in modes and ("nccl", "graph") in modes
+    for backend, engine in modes:
         for r in range(world):
             g = np.load(tmp_path / f"{backend}_{engine}_rank{r}.npz")
             assert list(g["ids"]) == want, (backend, engine, r)
             assert np.abs(g["logits"] - logits).max() < TOL
             got[backend, engine, r] = g["logits"].view(np.uint32)
     # rank-ordered sums: every rank, and both peer-memory engines, hold identical bits
-    ref = got["peer", "persistent", 0]
+    ref = got["peer", "graph", 0]
     for r in range(world):
-        assert np.array_equal(got["peer", "persistent", r], ref)
         assert np.array_equal(got["peer", "graph", r], ref)
+        if ("peer", "persistent") in modes:
+            assert np.array_equal(got["peer", "persistent", r], ref)
+    if key in ("small-tp", "small-tp-int8", "small-qwen"):
+        assert ("peer", "persistent") in modes, "the persistent engine must take this shape"
