@@ -157,6 +157,25 @@ __device__ __forceinline__ RowRef resolve_row(const Phase& ph, int unit, int sub
   return RowRef{seg, row};
 }
 
+// Row j of a ring stage that starts at unit u and holds n units, in STAGE ORDER.  SwiGLU stages
+// keep their w1 rows first and their w3 rows after them, so that each half -- like any run of
+// consecutive rows of one matrix -- is ONE contiguous span of the checkpoint and one bulk copy.
+__device__ __forceinline__ RowRef stage_row(const Phase& ph, int u, int n, int j) {
+  if (ph.swiglu) return j < n ? RowRef{0, u + j} : RowRef{1, u + j - n};
+  return resolve_row(ph, u + j, 0);
+}
+// Lane j (< nrows) holds row j of the stage: returns the length of the run of consecutive rows
+// of one matrix that STARTS at this lane (0 for lanes inside a run).
+__device__ __forceinline__ int run_length(const RowRef& rr, int lane, int nrows) {
+  const int pseg = __shfl_up_sync(kFull, rr.seg, 1);
+  const int prow = __shfl_up_sync(kFull, rr.row, 1);
+  const bool head = lane < nrows && (lane == 0 || rr.seg != pseg || rr.row != prow + 1);
+  const unsigned heads = __ballot_sync(kFull, head);
+  if (!head) return 0;
+  const unsigned later = heads & ~((2u << lane) - 1u);
+  return (later ? __ffs(later) - 1 : nrows) - lane;
+}
+
 // ---- exact-order accumulation from shared memory ----------------------------------------------
 // fp32: virtual thread (lane + 32 j) owns packs base + 32 j + lane (matmul_kernel.cu:27-35).
 // Full 128-pack blocks run branch-free with all 4*(1+NR) shared loads issued before the math
@@ -551,17 +570,20 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
               mbar_expect_tx(&full_bar[pipe.slot],
                              static_cast<uint32_t>(nrows) * (row_bytes + ph.scale_row_bytes));
             __syncwarp();
-            for (int i = lane; i < nrows; i += 32) {
-              const RowRef rr = resolve_row(ph, u + i / rpu, i % rpu);
-              const long long e = static_cast<long long>(rr.row) * ph.in_dim;
-              const unsigned char* src = static_cast<const unsigned char*>(ph.seg[rr.seg].w) + e * wbytes;
-              bulk_g2s(dst + static_cast<size_t>(i) * row_bytes, src, row_bytes,
-                       &full_bar[pipe.slot], policy);
-              if (ph.scale_row_bytes) {
-                const long long g0 = ph.group_shift >= 0 ? (e >> ph.group_shift) : (e / ph.group_size);
-                bulk_g2s(dst + ph.scale_off + static_cast<size_t>(i) * ph.scale_row_bytes,
-                         ph.seg[rr.seg].scales + g0, ph.scale_row_bytes, &full_bar[pipe.slot],
-                         policy);
+            {  // one bulk copy per run of consecutive rows of one matrix (nrows <= 32: lane = row)
+              const RowRef rr = lane < nrows ? stage_row(ph, u, n, lane) : RowRef{-1, -1};
+              const int len = run_length(rr, lane, nrows);
+              if (len > 0) {
+                const long long e = static_cast<long long>(rr.row) * ph.in_dim;
+                const unsigned char* src = static_cast<const unsigned char*>(ph.seg[rr.seg].w) + e * wbytes;
+                bulk_g2s(dst + static_cast<size_t>(lane) * row_bytes, src, static_cast<uint32_t>(len) * row_bytes,
+                         &full_bar[pipe.slot], policy);
+                if (ph.scale_row_bytes) {
+                  const long long g0 = ph.group_shift >= 0 ? (e >> ph.group_shift) : (e / ph.group_size);
+                  bulk_g2s(dst + ph.scale_off + static_cast<size_t>(lane) * ph.scale_row_bytes,
+                           ph.seg[rr.seg].scales + g0, static_cast<uint32_t>(len) * ph.scale_row_bytes,
+                           &full_bar[pipe.slot], policy);
+                }
               }
             }
             pipe.advance(S);
@@ -630,13 +652,18 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
           for (int u = u0; u < u1; u += ups) {
             const int nrows = min(ups, u1 - u) * rpu;
             throttle();
-            for (int i = lane; i < nrows; i += 32) {
-              const RowRef rr = resolve_row(ph, u + i / rpu, i % rpu);
-              const long long e = static_cast<long long>(rr.row) * ph.in_dim;
-              bulk_prefetch_l2(static_cast<const unsigned char*>(ph.seg[rr.seg].w) + e * wbytes, row_bytes);
-              if (ph.scale_row_bytes) {
-                const long long g0 = ph.group_shift >= 0 ? (e >> ph.group_shift) : (e / ph.group_size);
-                bulk_prefetch_l2(ph.seg[rr.seg].scales + g0, ph.scale_row_bytes);
+            {
+              const int n = nrows / rpu;
+              const RowRef rr = lane < nrows ? stage_row(ph, u, n, lane) : RowRef{-1, -1};
+              const int len = run_length(rr, lane, nrows);
+              if (len > 0) {
+                const long long e = static_cast<long long>(rr.row) * ph.in_dim;
+                bulk_prefetch_l2(static_cast<const unsigned char*>(ph.seg[rr.seg].w) + e * wbytes,
+                                 static_cast<uint32_t>(len) * row_bytes);
+                if (ph.scale_row_bytes) {
+                  const long long g0 = ph.group_shift >= 0 ? (e >> ph.group_shift) : (e / ph.group_size);
+                  bulk_prefetch_l2(ph.seg[rr.seg].scales + g0, static_cast<uint32_t>(len) * ph.scale_row_bytes);
+                }
               }
             }
             ++ahead;
@@ -901,8 +928,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
             const long long t_b = stamp ? clock64() : 0;
             if (P.group_size == 0) {
               if (ph.swiglu) {
-                const float4* w[2] = {reinterpret_cast<const float4*>(sbase + static_cast<size_t>(2 * i) * row_bytes),
-                                      reinterpret_cast<const float4*>(sbase + static_cast<size_t>(2 * i + 1) * row_bytes)};
+                const float4* w[2] = {reinterpret_cast<const float4*>(sbase + static_cast<size_t>(i) * row_bytes),
+                                      reinterpret_cast<const float4*>(sbase + static_cast<size_t>(n + i) * row_bytes)};
                 float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
                 accum_f32<2>(w, xs4, M >> 2, lane, acc);
                 const long long t_c = stamp ? clock64() : 0;
@@ -931,9 +958,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
                 const float* sc[2];
 #pragma unroll
                 for (int r = 0; r < 2; ++r) {
-                  w[r] = reinterpret_cast<const uint32_t*>(sbase + static_cast<size_t>(2 * i + r) * row_bytes);
+                  w[r] = reinterpret_cast<const uint32_t*>(sbase + static_cast<size_t>(r * n + i) * row_bytes);
                   sc[r] = reinterpret_cast<const float*>(sbase + ph.scale_off +
-                                                         static_cast<size_t>(2 * i + r) * ph.scale_row_bytes);
+                                                         static_cast<size_t>(r * n + i) * ph.scale_row_bytes);
                 }
                 float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
                 accum_w8<2>(w, sc, xs4, M, ph.group_shift, ph.group_size, lane, acc);
