@@ -105,6 +105,35 @@ __device__ __forceinline__ void ld_tagged2(const unsigned long long* p, unsigned
                                            unsigned long long& b) {
   asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
+// local (same GPU) flavour of the tagged words
+__device__ __forceinline__ void st_tagged_gpu(unsigned long long* p, float v, unsigned tag) {
+  const unsigned long long w = (static_cast<unsigned long long>(tag) << 32) | __float_as_uint(v);
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_tagged_gpu(const unsigned long long* p) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
+}
+__device__ __forceinline__ void ld_tagged2_gpu(const unsigned long long* p, unsigned long long& a,
+                                               unsigned long long& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+// spin until the word carries `tag` (bounded: a lost producer becomes a trap, not a hang)
+__device__ __forceinline__ float poll_tagged(const unsigned long long* p, unsigned tag) {
+  unsigned long long w = ld_tagged_gpu(p);
+  if (static_cast<unsigned>(w >> 32) != tag) {
+    const long long t0 = clock64();
+    do {
+      w = ld_tagged_gpu(p);
+      if (clock64() - t0 > 8000000000LL) {
+        printf("kllm mega: cta %d thread %d timed out on hand-off tag %u\n", blockIdx.x, threadIdx.x, tag);
+        __trap();
+      }
+    } while (static_cast<unsigned>(w >> 32) != tag);
+  }
+  return __uint_as_float(static_cast<unsigned>(w));
+}
 __device__ __forceinline__ void consumer_sync() {
   asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
 }
@@ -308,7 +337,8 @@ __device__ __forceinline__ int attn_tiles(int pos, int T) { return (pos + T - 1)
 
 __device__ void attention_phase(const Params& P, const Phase& ph, int head, int pos, float* ws,
                                 float* s_warp, float* s_bcast, unsigned char* stages,
-                                uint64_t* full_bar, uint64_t* empty_bar, Pipe& pipe) {
+                                uint64_t* full_bar, uint64_t* empty_bar, Pipe& pipe, unsigned tag_in,
+                                unsigned tag_out) {
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int hs = P.head_size, seq_len = P.seq_len, T = P.attn_tile, S = P.num_stages;
@@ -324,8 +354,10 @@ __device__ void attention_phase(const Params& P, const Phase& ph, int head, int 
   float* score_head = (pos + 1 <= smem_cap) ? (ws + 2 * hs) : (P.score + static_cast<size_t>(head) * seq_len);
 
   // value row of the current position (written by the QKV phase of this token)
+  const bool handoff = ph.tq != nullptr;  // q / k / v arrive as tagged words: no barrier before us
   float v_pos = 0.f;
-  if (tid < hs) v_pos = __ldcg(vcache + static_cast<size_t>(pos) * hs + tid);
+  if (tid < hs)
+    v_pos = handoff ? poll_tagged(ph.tv + kvh * hs + tid, tag_in) : __ldcg(vcache + static_cast<size_t>(pos) * hs + tid);
 
   // RoPE on q (this head) and on the new key row, rope_kernel.cu as compiled (elementwise.cu)
   if (tid < hs / 2) {
@@ -340,10 +372,12 @@ __device__ void attention_phase(const Params& P, const Phase& ph, int head, int 
     const int ci = 2 * tid;
     const float fci = P.sin_cache[static_cast<size_t>(pos) * hs + ci];
     const float fcr = P.cos_cache[static_cast<size_t>(pos) * hs + ci];
-    const float q0 = __ldcg(qg + i0), q1 = __ldcg(qg + i1);
+    const float q0 = handoff ? poll_tagged(ph.tq + head * hs + i0, tag_in) : __ldcg(qg + i0);
+    const float q1 = handoff ? poll_tagged(ph.tq + head * hs + i1, tag_in) : __ldcg(qg + i1);
     q_s[i0] = __fmaf_rn(fcr, q0, -__fmul_rn(fci, q1));
     q_s[i1] = __fmaf_rn(fci, q0, __fmul_rn(fcr, q1));
-    const float k0 = __ldcg(kg + i0), k1 = __ldcg(kg + i1);
+    const float k0 = handoff ? poll_tagged(ph.tk + kvh * hs + i0, tag_in) : __ldcg(kg + i0);
+    const float k1 = handoff ? poll_tagged(ph.tk + kvh * hs + i1, tag_in) : __ldcg(kg + i1);
     const float r0 = __fmaf_rn(fcr, k0, -__fmul_rn(fci, k1));
     const float r1 = __fmaf_rn(fci, k0, __fmul_rn(fcr, k1));
     k_s[i0] = r0;
@@ -448,7 +482,10 @@ __device__ void attention_phase(const Params& P, const Phase& ph, int head, int 
   }
   if (tid < hs) {
     value = __fmaf_rn(score_head[pos], v_pos, value);
-    P.attn_out[static_cast<size_t>(head) * hs + tid] = value;
+    if (ph.ta != nullptr)
+      st_tagged_gpu(ph.ta + static_cast<size_t>(head) * hs + tid, value, tag_out);
+    else
+      P.attn_out[static_cast<size_t>(head) * hs + tid] = value;
   }
 }
 
@@ -645,7 +682,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
         const int rpu = ph.swiglu ? 2 : 1;
         const int row_bytes = ph.in_dim * wbytes;
         auto throttle = [&]() {
-          while (static_cast<int>(ahead - s_fill_count) >= P.pf_stages) __nanosleep(64);
+          while (static_cast<int>(ahead - s_fill_count) >= P.pf_stages) __nanosleep(400);
         };
         if (ph.chunks_per_row == 1) {
           const int ups = ph.rows_per_stage / rpu;
@@ -700,6 +737,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
 
     const bool prof_on = P.prof != nullptr && tok == P.prof_token && tid == 0;
     bool prev_barrier = true;
+    auto hand_tag = [&](int hand) {
+      return P.hand_base + static_cast<unsigned>(tok * P.hands_per_token + hand) + 1u;
+    };
     for (int pi = 0; pi < P.n_phases; ++pi) {
       {
         // the grid barrier that ended the previous phase is the hazard fence for this copy; a
@@ -718,10 +758,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
 
       if (ph.kind == kPhaseAttention) {
         if (cta < P.head_num)
-          attention_phase(P, ph, cta, pos, xs, s_warp, &s_bcast, stages, full_bar, empty_bar, pipe);
+          attention_phase(P, ph, cta, pos, xs, s_warp, &s_bcast, stages, full_bar, empty_bar, pipe,
+                          hand_tag(ph.hand_in), hand_tag(ph.hand_out));
         if (stamp) stamp[1] = stamp[2] = global_ns();
-        grid_barrier(P.barrier, bar_target, G);
-        prev_barrier = true;
+        if (ph.barrier_after) grid_barrier(P.barrier, bar_target, G);
+        prev_barrier = ph.barrier_after != 0;
         if (stamp) stamp[3] = global_ns();
         continue;
       }
@@ -813,6 +854,43 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
         }
         consumer_sync();
       }
+      if (ph.tag_in != nullptr) {
+        // the previous phase's output vector, polled in place (no barrier in between)
+        const unsigned tag = hand_tag(ph.hand_in);
+        const int pairs = M >> 1;
+        const long long t_start = clock64();
+        for (int base = 0; base < pairs; base += 4 * kConsumerThreads) {
+          unsigned long long w[4][2];
+          bool ok;
+          do {
+            ok = true;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int pr = base + k * kConsumerThreads + tid;
+              if (pr < pairs) ld_tagged2_gpu(ph.tag_in + 2 * pr, w[k][0], w[k][1]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int pr = base + k * kConsumerThreads + tid;
+              if (pr < pairs)
+                ok = ok && static_cast<unsigned>(w[k][0] >> 32) == tag && static_cast<unsigned>(w[k][1] >> 32) == tag;
+            }
+            if (!ok && clock64() - t_start > 8000000000LL) {
+              printf("kllm mega: cta %d timed out on hand-off tag %u (phase input)\n", cta, tag);
+              __trap();
+            }
+          } while (!ok);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int pr = base + k * kConsumerThreads + tid;
+            if (pr < pairs) {
+              xs[2 * pr] = __uint_as_float(static_cast<unsigned>(w[k][0]));
+              xs[2 * pr + 1] = __uint_as_float(static_cast<unsigned>(w[k][1]));
+            }
+          }
+        }
+        consumer_sync();
+      }
       {
         const float* xg = ph.x_from_emb ? emb_row : ph.x;
         const float4* xg4 = reinterpret_cast<const float4*>(xg);
@@ -830,7 +908,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
             if (i < n4) nw[k] = __ldg(nw4 + i);
           }
         }
-        if (!ph.tp_in) {
+        if (!ph.tp_in && ph.tag_in == nullptr) {
           for (int i = tid; i < n4; i += kConsumerThreads) xs4w[i] = __ldcg(xg4 + i);
           consumer_sync();
         }
@@ -883,7 +961,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
       auto epilogue = [&](int unit, float d0, float d1, float bias_v, float res_v) {
         // lane 0 only
         if (ph.swiglu) {
-          ph.seg[0].out[unit] = swiglu_ref(d0, d1);
+          const float g = swiglu_ref(d0, d1);
+          if (ph.seg[0].tag_out != nullptr)
+            st_tagged_gpu(ph.seg[0].tag_out + unit, g, hand_tag(ph.hand_out));
+          else
+            ph.seg[0].out[unit] = g;
           return;
         }
         if (ph.tp_out) {
@@ -897,7 +979,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
         float v = d0;
         if (sg.bias != nullptr) v = __fadd_rn(v, bias_v);       // matmul.cpp:74-77: out + bias
         if (residual != nullptr) v = __fadd_rn(res_v, v);       // llama3.cpp:683,719: x + out
-        if (sg.head_major) {
+        if (sg.tag_out != nullptr) st_tagged_gpu(sg.tag_out + rr.row, v, hand_tag(ph.hand_out));
+        if (sg.out == nullptr) {
+        } else if (sg.head_major) {
           const int hs = P.head_size;
           sg.out[(static_cast<size_t>(rr.row / hs) * P.seq_len + pos) * hs + rr.row % hs] = v;
         } else {
@@ -1164,10 +1248,24 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
 
   // Tagged exchange instead of "write x, grid barrier, read x" after o_proj and down_proj:
   // mandatory under tensor parallelism (it IS the all-reduce), optional on one GPU.
+  // KLLM_MEGA_TAGGED = 0: grid barriers everywhere (one GPU only); 1: tagged residual exchange;
+  // 2 (default): + tagged hand-offs q|k|v -> attention -> Wo and SwiGLU -> W2, which leaves ONE
+  // grid barrier per token (after the classifier).
   const int W = m.tp_world > 1 ? m.tp_world : 1;
-  tagged_ = W > 1;
-  if (const char* e = getenv("KLLM_MEGA_TAGGED")) tagged_ = tagged_ || atoi(e) != 0;
-  else tagged_ = true;
+  tagged_mode_ = 2;
+  if (const char* e = getenv("KLLM_MEGA_TAGGED")) tagged_mode_ = std::min(2, std::max(0, atoi(e)));
+  if (W > 1 && tagged_mode_ == 0) tagged_mode_ = 1;
+  tagged_ = tagged_mode_ >= 1;
+  const bool handoffs = tagged_mode_ >= 2;
+  unsigned long long *t_q = nullptr, *t_k = nullptr, *t_v = nullptr, *t_attn = nullptr, *t_h = nullptr;
+  if (handoffs) {
+    const size_t words = static_cast<size_t>(2 * q_rows + 2 * kvd + hid);
+    if (cudaMalloc(&d_handoff_, sizeof(unsigned long long) * words) != cudaSuccess)
+      return static_cast<int>(cudaErrorMemoryAllocation);
+    cudaMemsetAsync(d_handoff_, 0, sizeof(unsigned long long) * words, stream);
+    t_q = d_handoff_, t_k = t_q + q_rows, t_v = t_k + kvd, t_attn = t_v + kvd, t_h = t_attn + q_rows;
+  }
+  int hands = 0;
   if (tagged_) {
     if (cudaMalloc(&d_xbuf_, sizeof(float) * 2 * dim) != cudaSuccess) return static_cast<int>(cudaErrorMemoryAllocation);
     cudaMemsetAsync(d_xbuf_, 0, sizeof(float) * 2 * dim, stream);
@@ -1229,14 +1327,25 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
                   m.value_cache + layer_off, 0, kvd, 1};
       p.units = q_rows + 2 * kvd;
       if (int rc = plan(p)) return rc;
-      close_phase(p, true);
+      if (handoffs) {  // q, raw k: tagged only; v: cache row (for later tokens) + tagged (for this one)
+        p.seg[0].out = nullptr, p.seg[0].tag_out = t_q;
+        p.seg[1].out = nullptr, p.seg[1].tag_out = t_k;
+        p.seg[2].tag_out = t_v;
+        p.hand_out = hands;
+      }
+      close_phase(p, !handoffs);
       ph.push_back(p);
     }
     {
       Phase p{};
       p.kind = mega::kPhaseAttention;
       p.layer = l;
-      close_phase(p, true);
+      if (handoffs) {
+        p.tq = t_q, p.tk = t_k, p.tv = t_v, p.ta = t_attn;
+        p.hand_in = hands++;
+        p.hand_out = hands;
+      }
+      close_phase(p, !handoffs);
       ph.push_back(p);
     }
     {  // wo + residual (llama3.cpp:672-684)
@@ -1247,6 +1356,11 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       p.x = m.attn_out;
       p.seg[0] = {m.wo[l], int8 ? m.so[l] : nullptr, nullptr, m.x, 0, dim, 0};
       p.units = dim;
+      if (handoffs) {
+        p.tag_in = t_attn;
+        p.hand_in = hands++;
+        p.x = nullptr;
+      }
       if (int rc = plan(p)) return rc;
       output_adds_to_x(p, l == 0);
       ph.push_back(p);
@@ -1264,7 +1378,11 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       p.seg[1] = {m.w3[l], int8 ? m.s3[l] : nullptr, nullptr, nullptr, 0, hid, 0};
       p.units = hid;
       if (int rc = plan(p)) return rc;
-      close_phase(p, true);
+      if (handoffs) {
+        p.seg[0].out = nullptr, p.seg[0].tag_out = t_h;
+        p.hand_out = hands;
+      }
+      close_phase(p, !handoffs);
       ph.push_back(p);
     }
     {  // w2 + residual (llama3.cpp:711-719)
@@ -1275,6 +1393,11 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       p.x = m.h;
       p.seg[0] = {m.w2[l], int8 ? m.s2[l] : nullptr, nullptr, m.x, 0, dim, 0};
       p.units = dim;
+      if (handoffs) {
+        p.tag_in = t_h;
+        p.hand_in = hands++;
+        p.x = nullptr;
+      }
       if (int rc = plan(p)) return rc;
       output_adds_to_x(p, false);
       ph.push_back(p);
@@ -1298,6 +1421,11 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   n_phases_ = static_cast<int>(ph.size());
   n_barriers_per_token_ = bars;
   exch_per_token_ = exch;
+  hands_per_token_ = hands;
+  // The producer streams K/V rows written by the PREVIOUS token once the grid barrier that closed
+  // that token's attention phase is passed; without such a barrier, the one that closed the token.
+  for (Phase& p : ph)
+    if (p.kind == mega::kPhaseAttention && !p.barrier_after) p.barrier_idx = bars;
 
   if (cudaMalloc(&d_phases_, sizeof(Phase) * ph.size()) != cudaSuccess) return static_cast<int>(cudaErrorMemoryAllocation);
   cudaMemcpyAsync(d_phases_, ph.data(), sizeof(Phase) * ph.size(), cudaMemcpyHostToDevice, stream);
@@ -1329,6 +1457,8 @@ void MegaEngine::destroy() {
   if (d_arg_idx_) cudaFree(d_arg_idx_);
   if (d_xbuf_) cudaFree(d_xbuf_);
   if (d_tagged_) cudaFree(d_tagged_);
+  if (d_handoff_) cudaFree(d_handoff_);
+  d_handoff_ = nullptr;
   d_xbuf_ = nullptr;
   d_tagged_ = nullptr;
   d_phases_ = nullptr;
@@ -1384,6 +1514,8 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
   if (m.tp_world <= 1) P.tp_data[0] = d_tagged_;
   P.exch_per_token = exch_per_token_;
   P.tp_seq_base = tp_seq_base_;
+  P.hand_base = hand_base_;
+  P.hands_per_token = hands_per_token_;
   P.arg_val = static_cast<float*>(d_arg_val_);
   P.arg_idx = static_cast<int*>(d_arg_idx_);
   P.prof = prof_dev;
@@ -1394,6 +1526,7 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
                                               stream_);
   if (e != cudaSuccess) return static_cast<int>(e);
   tp_seq_base_ += static_cast<unsigned>(n_tokens) * static_cast<unsigned>(exch_per_token_);
+  hand_base_ += static_cast<unsigned>(n_tokens) * static_cast<unsigned>(hands_per_token_);
   barrier_base_ += static_cast<unsigned>(n_tokens) * static_cast<unsigned>(n_barriers_per_token_) *
                    static_cast<unsigned>(grid_);
   count_launch();

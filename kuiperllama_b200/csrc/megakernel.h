@@ -18,6 +18,9 @@ struct Seg {
   long long pos_stride;
   int rows;
   int head_major;       // 1: out is the head-major value cache, index ((row/hs)*seq_len + pos)*hs + row%hs
+  // optional local hand-off: row r is (also) published as a tagged 64-bit word at tag_out[r] for
+  // the next phase to poll (out may then be null)
+  unsigned long long* tag_out;
 };
 
 // One entry of the per-token schedule.  A GEMV phase's units (rows, or w1/w3 row pairs) are
@@ -53,6 +56,16 @@ struct Phase {
   int barrier_idx;        // barriers of this token passed once this phase is closed
   const float* x_old;     // tp_in: residual stream before the exchange (nullptr: the embedding row)
   float* x_new;           // tp_in: residual stream after it
+  // Local tagged hand-offs (same words, one rank): the phase's input vector is polled from tag_in
+  // (GEMV) or tq/tk/tv (attention: this head's query, its kv head's raw key and value rows);
+  // outputs go to seg[].tag_out (GEMV) or ta (attention).  hand_in / hand_out number the
+  // hand-offs of a token for the tags.
+  const unsigned long long* tag_in;
+  const unsigned long long* tq;
+  const unsigned long long* tk;
+  const unsigned long long* tv;
+  unsigned long long* ta;
+  int hand_in, hand_out;
   Seg seg[3];
 };
 
@@ -91,6 +104,8 @@ struct Params {
   unsigned long long* tp_data[8];
   int tp_world, tp_rank, tp_stride, exch_per_token;
   unsigned tp_seq_base;
+  unsigned hand_base;
+  int hands_per_token;
   float* arg_val;
   int* arg_idx;
   // optional phase timeline of one token: prof[(cta * n_phases + phase) * 4 + k], k = phase
@@ -152,9 +167,11 @@ class MegaEngine {
   void* d_arg_idx_ = nullptr;
   float* d_xbuf_ = nullptr;                // [2][dim]: the residual stream, alternating per exchange
   unsigned long long* d_tagged_ = nullptr;  // single-GPU exchange area (tp_world == 1)
+  unsigned long long* d_handoff_ = nullptr;  // local tagged hand-off vectors (q | k | v | attn | h)
   bool tagged_ = false;
-  int exch_per_token_ = 0;
-  unsigned tp_seq_base_ = 0;
+  int tagged_mode_ = 0;  // 0: grid barriers everywhere; 1: tagged residual exchange; 2: + tagged hand-offs
+  int exch_per_token_ = 0, hands_per_token_ = 0;
+  unsigned tp_seq_base_ = 0, hand_base_ = 0;
   int grid_ = 0, stages_ = 0, stage_bytes_ = 0, xbuf_bytes_ = 0, n_phases_ = 0, attn_tile_ = 0;
   int n_barriers_per_token_ = 0;
   size_t smem_bytes_ = 0;
