@@ -39,22 +39,45 @@ def kv_heads_of_rank(shape: ModelShape, tp: int, rank: int) -> range:
     return range(kv, kv + 1)
 
 
+# int8 FFN shards are cut in units of 256 columns: whole quantisation groups (64) AND 16-byte rows of
+# group scales per shard, which is what the persistent engine's TMA ring can stage
+INT8_FFN_UNIT = 256
+
+
+def ffn_range(shape: ModelShape, tp: int, rank: int) -> range:
+    """FFN rows (w1 / w3 output rows = w2 input columns) rank `rank` owns.  fp32: equal slices.
+    int8: multiples of INT8_FFN_UNIT, spread as evenly as they go (Llama-2-7B: 11008 = 43 units ->
+    5632 + 5376 at tp 2), so ranks may differ by one unit."""
+    h = shape.hidden_dim
+    if not shape.group_size:
+        n = h // tp
+        return range(rank * n, (rank + 1) * n)
+    units = h // INT8_FFN_UNIT
+    base, extra = divmod(units, tp)
+    start = rank * base + min(rank, extra)
+    return range(start * INT8_FFN_UNIT, (start + base + (1 if rank < extra else 0)) * INT8_FFN_UNIT)
+
+
 def check_shardable(shape: ModelShape, tp: int) -> None:
     s = shape
-    if tp < 1 or s.head_num % tp or s.hidden_dim % tp:
-        raise KllmError(f"{s.name}: {s.head_num} heads / hidden {s.hidden_dim} do not split {tp} ways")
+    if tp < 1 or s.head_num % tp:
+        raise KllmError(f"{s.name}: {s.head_num} heads do not split {tp} ways")
+    if s.group_size:
+        if s.hidden_dim % INT8_FFN_UNIT or s.hidden_dim // INT8_FFN_UNIT < tp:
+            raise KllmError(f"{s.name}: int8 hidden_dim {s.hidden_dim} does not split {tp} ways in units of "
+                            f"{INT8_FFN_UNIT} columns")
+    elif s.hidden_dim % tp:
+        raise KllmError(f"{s.name}: hidden {s.hidden_dim} does not split {tp} ways")
     if s.kv_head_num >= tp:
         if s.kv_head_num % tp:
             raise KllmError(f"{s.name}: {s.kv_head_num} kv heads do not split {tp} ways")
     elif tp % s.kv_head_num or (s.head_num // tp) > s.kv_mul or s.kv_mul % (s.head_num // tp):
         raise KllmError(f"{s.name}: cannot replicate {s.kv_head_num} kv heads over {tp} ranks")
-    if (s.hidden_dim // tp) % 4:
+    if not s.group_size and (s.hidden_dim // tp) % 4:
         raise KllmError(f"{s.name}: hidden_dim/{tp} must be a multiple of 4")
-    if s.group_size:
-        for cols in (s.head_num // tp * s.head_size, s.hidden_dim // tp):
-            if cols % s.group_size:
-                raise KllmError(f"{s.name}: int8 groups of {s.group_size} straddle the {tp}-way column "
-                                f"split ({cols} columns per rank)")
+    if s.group_size and (s.head_num // tp * s.head_size) % s.group_size:
+        raise KllmError(f"{s.name}: int8 groups of {s.group_size} straddle the {tp}-way split of the "
+                        f"attention columns ({s.head_num // tp * s.head_size} per rank)")
 
 
 def local_shape(shape: ModelShape, tp: int, rank: int = 0) -> ModelShape:
@@ -62,7 +85,7 @@ def local_shape(shape: ModelShape, tp: int, rank: int = 0) -> ModelShape:
     model dim (include/kllm_b200.h, tp fields)."""
     check_shardable(shape, tp)
     return replace(shape, name=f"{shape.name}[tp{tp}]", head_num=shape.head_num // tp,
-                   kv_head_num=len(kv_heads_of_rank(shape, tp, rank)), hidden_dim=shape.hidden_dim // tp)
+                   kv_head_num=len(kv_heads_of_rank(shape, tp, rank)), hidden_dim=len(ffn_range(shape, tp, rank)))
 
 
 def weight_bytes_per_token_per_gpu(shape: ModelShape, tp: int, rank: int = 0) -> int:
@@ -73,7 +96,7 @@ def weight_bytes_per_token_per_gpu(shape: ModelShape, tp: int, rank: int = 0) ->
     s = shape
     d, L, V, hs = s.dim, s.layer_num, s.vocab_size, s.head_size
     kv_rows = len(kv_heads_of_rank(s, tp, rank)) * hs
-    numel = L * (2 * d * d // tp + 2 * kv_rows * d + 3 * (s.hidden_dim // tp) * d) + V * d
+    numel = L * (2 * d * d // tp + 2 * kv_rows * d + 3 * len(ffn_range(s, tp, rank)) * d) + V * d
     wbytes = numel * 4 if s.group_size == 0 else numel + numel // s.group_size * 4
     extra = (2 * L + 1) * d * 4 + d * 4
     if s.flavour == "qwen2" and s.group_size == 0:
@@ -93,7 +116,8 @@ def shard_weights(shape: ModelShape, w: dict, tp: int, rank: int) -> dict:
     q0, q1 = rank * (s.head_num // tp) * hs, (rank + 1) * (s.head_num // tp) * hs
     kvh = kv_heads_of_rank(s, tp, rank)
     k0, k1 = kvh.start * hs, kvh.stop * hs
-    f0, f1 = rank * (s.hidden_dim // tp), (rank + 1) * (s.hidden_dim // tp)
+    ffn = ffn_range(s, tp, rank)
+    f0, f1 = ffn.start, ffn.stop
     out = {k: w[k] for k in ("tok_emb", "attn_norm", "ffn_norm", "final_norm", "wcls") if k in w}
     rows = {"wq": (q0, q1), "wk": (k0, k1), "wv": (k0, k1), "w1": (f0, f1), "w3": (f0, f1)}
     cols = {"wo": (q0, q1), "w2": (f0, f1)}

@@ -58,7 +58,17 @@ def test_unshardable_shapes_are_refused():
     with pytest.raises(KllmError):
         check_shardable(SHAPES["small"], 2)          # 9 heads
     with pytest.raises(KllmError):
-        check_shardable(SHAPES["llama2-7b-int8"], 8)  # 1376 columns per rank straddle int8 groups
+        check_shardable(SHAPES["tiny-int8"], 2)       # hidden 384: not a multiple of 256 int8 columns
+    # int8 FFN shards: whole units of 256 columns, ranks may differ by one unit
+    from kuiperllama_b200.tensor_parallel import ffn_range
+    s7 = SHAPES["llama2-7b-int8"]
+    assert [len(ffn_range(s7, 2, r)) for r in range(2)] == [5632, 5376]
+    for tp in (2, 4, 8):
+        check_shardable(s7, tp)
+        cuts = [ffn_range(s7, tp, r) for r in range(tp)]
+        assert cuts[0].start == 0 and cuts[-1].stop == s7.hidden_dim
+        assert all(a.stop == b.start for a, b in zip(cuts, cuts[1:]))
+        assert all(len(c) % 256 == 0 for c in cuts)
     check_shardable(SHAPES["tinyllama-1.1b"], 8)      # 4 kv heads replicated over 8 ranks
     check_shardable(SHAPES["llama2-7b"], 8)
 
