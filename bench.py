@@ -304,6 +304,7 @@ def run_ours(args, rank, world):
         tok = dec.step(tok, pos)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches_e2e0 = lib.kllm_launch_count()
     e2.record(stream)
     tok, ids_e2e = 1, []
     for pos in range(K):
@@ -312,6 +313,7 @@ def run_ours(args, rank, world):
     e3.record(stream)
     barrier()
     ms_e2e = e2.elapsed_time(e3)
+    launches_e2e = lib.kllm_launch_count() - launches_e2e0
     if ids_e2e != ids:
         raise SystemExit("e2e path produced different token ids than the device-resident loop")
 
@@ -352,7 +354,11 @@ def run_ours(args, rank, world):
                    "launches_per_step": dec_launches if comm else dec.launches_per_step},
         "e2e": {"value": K / (ms_e2e / 1e3), "unit": "tokens/s", "h2d_bytes_per_step": 16,
                 "d2h_bytes_per_step": 16},
+        # kernels of libkllm_b200 launched inside the timed region of `value`: the persistent engine
+        # decodes all K positions in ONE cooperative launch (the graph engine: K x launches_per_step);
+        # the e2e region launches once per token
         "gpu_launches": int(launches),
+        "gpu_launches_e2e": int(launches_e2e),
         "clocks": clocks,
     }
     if world > 1:
