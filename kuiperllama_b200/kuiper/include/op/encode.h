@@ -1,7 +1,11 @@
 // Tokenizer "layers" (reference op/encode.h).  Tokenisation is not on the decode hot path and its
-// third-party stack (sentencepiece, re2, abseil, nlohmann_json) is not vendored: with
-// -DKLLM_WITH_SENTENCEPIECE the SentencePiece model is used, otherwise a deterministic id-level
-// stand-in keeps Model::init working for synthetic checkpoints (ids in, "<id>" text out).
+// third-party stack (sentencepiece, re2, abseil, nlohmann_json) is not vendored.
+//   SpeEncodeLayer: SentencePiece BPE models (Llama-2 / TinyLlama `tokenizer.model`) are read by
+//     the library's own implementation (op/spm_bpe.h), or by libsentencepiece when built with
+//     -DKLLM_WITH_SENTENCEPIECE.  The path "<none>" (or an empty one) selects a deterministic
+//     id-level stand-in for synthetic checkpoints (ids in, "<id>" text out); any other path that
+//     cannot be loaded is fatal, as in the reference (encode.cpp:24-34).
+//   BpeEncodeLayer / QwenEncodeLayer (tiktoken-style tokenizer.json): stand-in only.
 #ifndef KLLM_KUIPER_OP_ENCODE_H_
 #define KLLM_KUIPER_OP_ENCODE_H_
 #include <memory>
@@ -11,6 +15,8 @@
 #include "layer.h"
 #ifdef KLLM_WITH_SENTENCEPIECE
 #include <sentencepiece_processor.h>
+#else
+#include "spm_bpe.h"
 #endif
 namespace op {
 class EncodeLayerBase : public Layer {
@@ -44,6 +50,8 @@ class SpeEncodeLayer : public EncodeLayerBase {
  private:
 #ifdef KLLM_WITH_SENTENCEPIECE
   std::unique_ptr<sentencepiece::SentencePieceProcessor> spe;
+#else
+  std::unique_ptr<SpmBpeModel> spm_;  // null: the id-level stand-in
 #endif
   int32_t stub_vocab_ = 32000;
 };

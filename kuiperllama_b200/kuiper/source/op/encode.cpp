@@ -31,8 +31,16 @@ SpeEncodeLayer::SpeEncodeLayer(std::string token_model_path, bool has_bos, bool 
     LOG(FATAL) << "The token model path is not valid, please check the path and type of token model.";
   }
 #else
-  LOG(INFO) << "SentencePiece support not compiled in: using the id-level stand-in tokenizer for "
-            << token_model_path_;
+  if (token_model_path_.empty() || token_model_path_ == "<none>") {
+    LOG(INFO) << "no tokenizer model given: using the id-level stand-in tokenizer";
+    return;
+  }
+  spm_ = std::make_unique<SpmBpeModel>();
+  const std::string err = spm_->load(token_model_path_);
+  if (!err.empty()) {
+    LOG(FATAL) << "The token model path is not valid, please check the path and type of token model: "
+               << token_model_path_ << ": " << err;
+  }
 #endif
 }
 
@@ -43,7 +51,11 @@ std::vector<int32_t> SpeEncodeLayer::encode(const std::string& sentence) const {
   if (has_eos_) ids.push_back(spe->eos_id());
   return ids;
 #else
-  return bytes_to_ids(sentence, has_bos_, has_eos_, stub_vocab_);
+  if (!spm_) return bytes_to_ids(sentence, has_bos_, has_eos_, stub_vocab_);
+  std::vector<int32_t> ids = spm_->encode(sentence);
+  if (has_bos_) ids.insert(ids.begin(), spm_->bos_id());
+  if (has_eos_) ids.push_back(spm_->eos_id());
+  return ids;
 #endif
 }
 
@@ -53,7 +65,7 @@ std::string SpeEncodeLayer::decode(const std::vector<int32_t>& token_ids) const 
 #ifdef KLLM_WITH_SENTENCEPIECE
   return spe->DecodeIds(token_ids);
 #else
-  return ids_to_text(token_ids);
+  return spm_ ? spm_->decode(token_ids) : ids_to_text(token_ids);
 #endif
 }
 
@@ -61,8 +73,8 @@ bool SpeEncodeLayer::is_sentence_ending(int32_t token_id) const {
 #ifdef KLLM_WITH_SENTENCEPIECE
   return token_id == spe->eos_id();
 #else
-  UNUSED(token_id);
-  return false;  // synthetic checkpoints: always decode the requested number of steps
+  // stand-in (synthetic checkpoints): always decode the requested number of steps
+  return spm_ ? token_id == spm_->eos_id() : false;
 #endif
 }
 
@@ -70,7 +82,7 @@ int32_t SpeEncodeLayer::vocab_size() const {
 #ifdef KLLM_WITH_SENTENCEPIECE
   return spe->GetPieceSize();
 #else
-  return stub_vocab_;
+  return spm_ ? spm_->piece_size() : stub_vocab_;
 #endif
 }
 

@@ -1,0 +1,133 @@
+"""The library's own SentencePiece-BPE tokenizer (kuiper/source/op/spm_bpe.cpp behind
+op::SpeEncodeLayer, the front end of model::LLama2Model::encode / decode) against the SentencePiece
+Python package: a Llama-style model (BPE, byte fallback, identity normalisation, dummy prefix) is
+trained here on a small corpus, then ids and decoded text must match exactly."""
+import random
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+sys.path.insert(0, str(ROOT / "kuiperllama_b200" / "kuiper"))
+import build_host  # noqa: E402
+
+spm = pytest.importorskip("sentencepiece")
+
+
+def _corpus():
+    import this  # noqa: F401  (the Zen of Python, rot13 in this.s)
+    import codecs
+    import inspect
+    import json as _json
+    import textwrap
+    text = [codecs.decode(this.s, "rot13")]
+    for mod in (textwrap, _json, inspect, random, subprocess):
+        text.append(inspect.getsource(mod))
+    extra = ["Once upon a time, there was a little girl named Lily. She loved to play outside.",
+             "naïve café déjà vu — über straße", "東京は日本の首都です。", "Привет, мир! Как дела?",
+             "1234567890 3.14159 2^10 = 1024", "tabs\tand  double  spaces   here"]
+    return "\n".join(text).splitlines() + extra * 20
+
+
+@pytest.fixture(scope="module")
+def models(tmp_path_factory):
+    d = tmp_path_factory.mktemp("spm")
+    corpus = d / "corpus.txt"
+    corpus.write_text("\n".join(l for l in _corpus() if l.strip()), encoding="utf-8")
+    out = {}
+    # (a) the Llama-2 recipe: BPE, byte fallback, identity normaliser, digits split, no squeezing
+    spm.SentencePieceTrainer.train(
+        input=str(corpus), model_prefix=str(d / "llama_like"), vocab_size=900, model_type="bpe",
+        byte_fallback=True, normalization_rule_name="identity", add_dummy_prefix=True,
+        remove_extra_whitespaces=False, split_digits=True, character_coverage=0.995,
+        allow_whitespace_only_pieces=True, minloglevel=2)
+    out["llama_like"] = d / "llama_like.model"
+    # (b) no byte fallback, whitespace squeezing on: unknown characters become <unk>
+    spm.SentencePieceTrainer.train(
+        input=str(corpus), model_prefix=str(d / "plain"), vocab_size=500, model_type="bpe",
+        byte_fallback=False, normalization_rule_name="identity", remove_extra_whitespaces=True,
+        character_coverage=0.98, minloglevel=2)
+    out["plain"] = d / "plain.model"
+    # (c) what must be refused: a unigram model
+    spm.SentencePieceTrainer.train(
+        input=str(corpus), model_prefix=str(d / "unigram"), vocab_size=400, model_type="unigram",
+        normalization_rule_name="identity", minloglevel=2)
+    out["unigram"] = d / "unigram.model"
+    return out
+
+
+def _exe():
+    exe = build_host.binary("llama2", "kuiper_tokenize")
+    if not exe.exists():
+        build_host.build("llama2")
+    return str(exe)
+
+
+def _sentences():
+    rng = random.Random(7)
+    base = [
+        "Hello world", "hello", " leading space", "trailing space ", "two  spaces", "   ", "a", "",
+        "Once upon a time, there was a little girl named Lily.", "The quick brown fox jumps over the lazy dog!",
+        "naïve café — déjà vu", "東京は日本の首都です。", "Привет, мир!", "emoji 🙂 and 🚀 rockets",
+        "mixed 東京 and English 123", "tab\there", "line one\\nline two", "x = y ** 2 + 3.14159;",
+        "def f(a, b):\\n    return a + b", "ÿþý odd latin-1 letters", "▁ the blank symbol itself",
+        "UPPER lower MiXeD", "a" * 50, "ab" * 40, "!!!???...", "https://example.com/path?q=1&r=2",
+    ]
+    words = ("the of and to in is it you that he was for on are with as his they be at one have this from or had by "
+             "hot word but what some we can out other were all there when up use your how said an each she").split()
+    for _ in range(60):
+        base.append(" ".join(rng.choice(words) for _ in range(rng.randint(1, 14))))
+    for _ in range(30):  # random unicode soup
+        base.append("".join(chr(rng.choice([rng.randint(32, 126), rng.randint(0xA1, 0x17F), rng.randint(0x400, 0x44F),
+                                                rng.randint(0x4E00, 0x4E80), 0x20])) for _ in range(rng.randint(1, 30))))
+    return base
+
+
+@pytest.mark.parametrize("name", ["llama_like", "plain"])
+def test_encode_and_decode_match_sentencepiece(models, name):
+    sp = spm.SentencePieceProcessor(model_file=str(models[name]))
+    sents = [s for s in _sentences() if "\n" not in s]
+    payload = "\n".join(sents) + "\n"
+    r = subprocess.run([_exe(), str(models[name]), "encode"], input=payload, capture_output=True, text=True,
+                       timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = [[int(t) for t in line.split()] for line in r.stdout.split("\n")[:len(sents)]]
+    assert len(got) == len(sents)
+    all_ids = []
+    for s, ids in zip(sents, got):
+        want = [sp.bos_id()] + sp.encode(s.replace("\\n", "\n"))
+        assert ids == want, (name, s)
+        all_ids.append(want)
+    # decode: whole sentences, their BOS-less tails, and every single id of the vocabulary
+    cases = all_ids + [ids[1:] for ids in all_ids] + [[i] for i in range(sp.get_piece_size())]
+    rng = random.Random(11)  # arbitrary id sequences: byte pieces, control pieces and blanks in any order
+    cases += [[rng.randrange(sp.get_piece_size()) for _ in range(rng.randint(1, 12))] for _ in range(400)]
+    cases += [[rng.randrange(min(270, sp.get_piece_size())) for _ in range(rng.randint(1, 8))] for _ in range(300)]
+    cases = [c for c in cases if c]
+    r = subprocess.run([_exe(), str(models[name]), "decode"],
+                       input="\n".join(" ".join(map(str, c)) for c in cases) + "\n", capture_output=True,
+                       text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.split("\n")[:len(cases)]
+    for c, line in zip(cases, lines):
+        assert bytes.fromhex(line) == sp.decode(c).encode("utf-8"), (name, c)
+
+
+def test_info_and_eos(models):
+    sp = spm.SentencePieceProcessor(model_file=str(models["llama_like"]))
+    r = subprocess.run([_exe(), str(models["llama_like"]), "info"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.split() == ["vocab", str(sp.get_piece_size()), "eos_is_2", "1"]
+
+
+def test_unsupported_or_missing_models_are_fatal(models, tmp_path):
+    for path in (models["unigram"], tmp_path / "missing.model"):
+        r = subprocess.run([_exe(), str(path), "info"], capture_output=True, text=True, timeout=60)
+        assert r.returncode != 0
+        assert "token model path is not valid" in r.stderr
+    junk = tmp_path / "junk.model"
+    junk.write_bytes(b"\x00\x01not a protobuf at all" * 10)
+    r = subprocess.run([_exe(), str(junk), "info"], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0
