@@ -54,6 +54,16 @@ def test_host_library_builds_and_reference_demos_link_unchanged(kllm_lib, varian
     assert "libkllm_b200.so" in ldd
 
 
+def test_host_api_selftest_cpu_cases(kllm_lib):
+    """tools/kuiper_selftest.cpp: the CPU cases of the reference's gtest programs for Buffer / Tensor
+    (test/test_tensor/*.cpp) plus Status, layer check() and checkpoint-header behaviour."""
+    out = build_host.build("llama2")
+    r = subprocess.run([str(out / "kuiper_selftest"), str(GOLDEN / "tiny_llama2_fp32.bin")], capture_output=True,
+                       text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failed expectation(s)" in r.stdout and "FAILED" not in r.stdout
+
+
 def test_host_fails_loudly_without_a_gpu(kllm_lib):
     import torch
     if torch.cuda.is_available():
