@@ -8,13 +8,21 @@
 // and a dedicated producer warp streams that CTA's share of EVERY weight matrix, in schedule
 // order, through a ring of shared-memory stages with TMA bulk copies (cp.async.bulk ->
 // UBLKCP) signalled on mbarriers.  Weights never depend on activations, so the producer runs
-// ahead across phase boundaries, grid barriers and the attention phase: HBM keeps streaming
-// while consumers wait for each other, and the ~190 KB/SM of ring (28 MB chip-wide, ~4 us of
-// HBM time) absorbs every such stall.
+// ahead across every dependency of the token; a second producer warp walks the same schedule a
+// few stages further ahead and only pulls the bytes into L2 (cp.async.bulk.prefetch.L2), so
+// HBM keeps fetching while SMs wait for each other.
 //
-// Schedule per layer (5 grid barriers):  QKV(+bias) | attention(+RoPE) | Wo+residual |
-// W1,W3->SiLU*gate | W2+residual ; then classifier + greedy argmax.  RoPE moves into the
-// attention phase so GEMV rows can be split evenly over all SMs.
+// Schedule per layer:  QKV(+bias) | attention(+RoPE) | Wo | W1,W3->SiLU*gate | W2 ; then
+// classifier + greedy argmax.  RoPE moves into the attention phase so GEMV rows can be split
+// evenly over all SMs.
+//
+// Hand-over between phases (KLLM_MEGA_TAGGED=2, default): every produced element is published as
+// one 64-bit {tag, fp32} word and polled in place by the consuming phase -- no fences, flags or
+// grid barriers; the residual-stream update after Wo and W2 is summed by the reader
+// (x = x_old + sum over ranks), which under tensor parallelism makes the same stores, sent to
+// every rank over NVLink peer mappings, the all-reduce.  One grid barrier per token remains
+// (before the argmax fold).  KLLM_MEGA_TAGGED=1 keeps grid barriers for the hand-offs inside a
+// layer, 0 uses grid barriers everywhere (single GPU only).
 //
 // Arithmetic is the same as the per-op kernels (gemv.cu / attention.cu / elementwise.cu): every
 // dot product, reduction tree, softmax sum and value chain reproduces the reference CUDA
