@@ -5,7 +5,8 @@
 //     -DKLLM_WITH_SENTENCEPIECE.  The path "<none>" (or an empty one) selects a deterministic
 //     id-level stand-in for synthetic checkpoints (ids in, "<id>" text out); any other path that
 //     cannot be loaded is fatal, as in the reference (encode.cpp:24-34).
-//   BpeEncodeLayer / QwenEncodeLayer (tiktoken-style tokenizer.json): stand-in only.
+//   BpeEncodeLayer / QwenEncodeLayer: byte-level BPE `tokenizer.json` files (Llama-3, Qwen2) are
+//     read by the library's own implementation (op/byte_bpe.h); "<none>" selects the stand-in.
 #ifndef KLLM_KUIPER_OP_ENCODE_H_
 #define KLLM_KUIPER_OP_ENCODE_H_
 #include <memory>
@@ -18,6 +19,7 @@
 #else
 #include "spm_bpe.h"
 #endif
+#include "byte_bpe.h"
 namespace op {
 class EncodeLayerBase : public Layer {
  public:
@@ -56,9 +58,10 @@ class SpeEncodeLayer : public EncodeLayerBase {
   int32_t stub_vocab_ = 32000;
 };
 
-// tiktoken-style BPE front ends (Llama-3 / Qwen2 tokenizer.json).  Stand-in only, see above.
+// Byte-level BPE front ends (Llama-3 / Qwen2 tokenizer.json; reference encode.cpp:62-180).
 class BpeEncodeLayer : public EncodeLayerBase {
  public:
+  // Llama-3 special tokens: <|begin_of_text|>, <|end_of_text|>, <|eot_id|>
   explicit BpeEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos);
   std::vector<int32_t> encode(const std::string& sentence) const override;
   std::string decode(int32_t token_id) const override;
@@ -67,11 +70,17 @@ class BpeEncodeLayer : public EncodeLayerBase {
   int32_t vocab_size() const override;
 
  protected:
+  // shared by the two families: load the file, look the three special tokens up
+  BpeEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos, const char* bos, const char* eos,
+                 const char* stop2, int32_t stub_vocab);
+  std::unique_ptr<ByteBpeModel> bpe_;  // null: the id-level stand-in
   int32_t bos_id_ = -1;
   int32_t eos_id_ = -1;
+  int32_t stop_token1_ = -1, stop_token2_ = -1;
   int32_t num_token_ = 0;
 };
 
+// Qwen2 special tokens: <|im_start|>, <|im_end|>, <|endoftext|>
 class QwenEncodeLayer : public BpeEncodeLayer {
  public:
   explicit QwenEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos);

@@ -86,21 +86,50 @@ int32_t SpeEncodeLayer::vocab_size() const {
 #endif
 }
 
-BpeEncodeLayer::BpeEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos)
+BpeEncodeLayer::BpeEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos, const char* bos,
+                               const char* eos, const char* stop2, int32_t stub_vocab)
     : EncodeLayerBase(std::move(token_model_path), has_bos, has_eos) {
-  bos_id_ = 1;
-  eos_id_ = 2;
-  num_token_ = 151936;  // overwritten by the checkpoint header (model.cpp:149)
-  LOG(INFO) << "tiktoken/BPE support is not part of this library: using the id-level stand-in tokenizer.";
+  if (token_model_path_.empty() || token_model_path_ == "<none>") {
+    bos_id_ = 1, eos_id_ = 2;
+    num_token_ = stub_vocab;  // overwritten by the checkpoint header (model.cpp)
+    LOG(INFO) << "no tokenizer.json given: using the id-level stand-in tokenizer";
+    return;
+  }
+  bpe_ = std::make_unique<ByteBpeModel>();
+  const std::string err = bpe_->load(token_model_path_);
+  if (!err.empty()) {
+    LOG(FATAL) << "The token model path is not valid, please check the path and type of token model: "
+               << token_model_path_ << ": " << err;
+  }
+  bos_id_ = bpe_->token_to_id(bos);
+  eos_id_ = bpe_->token_to_id(eos);
+  stop_token1_ = eos_id_;
+  stop_token2_ = bpe_->token_to_id(stop2);
+  num_token_ = bpe_->vocab_size();
 }
+
+BpeEncodeLayer::BpeEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos)
+    : BpeEncodeLayer(std::move(token_model_path), has_bos, has_eos, "<|begin_of_text|>", "<|end_of_text|>",
+                     "<|eot_id|>", 128256) {}
+
 std::vector<int32_t> BpeEncodeLayer::encode(const std::string& sentence) const {
-  return bytes_to_ids(sentence, has_bos_, has_eos_, num_token_);
+  if (!bpe_) return bytes_to_ids(sentence, has_bos_, has_eos_, num_token_);
+  std::vector<int32_t> ids = bpe_->encode(sentence);
+  if (has_bos_ && bos_id_ >= 0) ids.insert(ids.begin(), bos_id_);
+  if (has_eos_ && eos_id_ >= 0) ids.push_back(eos_id_);
+  return ids;
 }
-std::string BpeEncodeLayer::decode(int32_t token_id) const { return ids_to_text({token_id}); }
-std::string BpeEncodeLayer::decode(const std::vector<int32_t>& token_ids) const { return ids_to_text(token_ids); }
-bool BpeEncodeLayer::is_sentence_ending(int32_t) const { return false; }
+std::string BpeEncodeLayer::decode(int32_t token_id) const { return decode(std::vector<int32_t>{token_id}); }
+std::string BpeEncodeLayer::decode(const std::vector<int32_t>& token_ids) const {
+  return bpe_ ? bpe_->decode(token_ids) : ids_to_text(token_ids);
+}
+bool BpeEncodeLayer::is_sentence_ending(int32_t token_id) const {
+  // stand-in (synthetic checkpoints): always decode the requested number of steps
+  return bpe_ != nullptr && token_id >= 0 && (token_id == stop_token1_ || token_id == stop_token2_);
+}
 int32_t BpeEncodeLayer::vocab_size() const { return num_token_; }
 
 QwenEncodeLayer::QwenEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos)
-    : BpeEncodeLayer(std::move(token_model_path), has_bos, has_eos) {}
+    : BpeEncodeLayer(std::move(token_model_path), has_bos, has_eos, "<|im_start|>", "<|im_end|>", "<|endoftext|>",
+                     151936) {}
 }  // namespace op

@@ -1,6 +1,8 @@
 // kuiper_tokenize: exercise op::SpeEncodeLayer (the tokenizer front end of model::LLama2Model) from
 // the command line; the tokenizer tests compare it with the SentencePiece Python package.
 //
+//   kuiper_tokenize [--llama3|--qwen] <tokenizer file> <mode>   (default: SentencePiece tokenizer.model;
+//                   --llama3 / --qwen: byte-level BPE tokenizer.json through Bpe/QwenEncodeLayer)
 //   kuiper_tokenize <tokenizer.model> encode   < lines of text      -> one line of ids per input line
 //   kuiper_tokenize <tokenizer.model> decode   < lines of ids       -> one line of hex-encoded UTF-8 text per input line
 //   kuiper_tokenize <tokenizer.model> info                          -> vocab size, bos, eos
@@ -10,6 +12,7 @@
 
 #include <cstdio>
 #include <iostream>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -17,12 +20,22 @@
 #include "op/encode.h"
 
 int main(int argc, char** argv) {
+  std::string family = "spe";
+  if (argc > 1 && std::string(argv[1]).rfind("--", 0) == 0) {
+    family = argv[1] + 2;
+    --argc, ++argv;
+  }
   if (argc < 3) {
-    std::fprintf(stderr, "usage: %s <tokenizer.model> encode|decode|info\n", argv[0]);
+    std::fprintf(stderr, "usage: %s [--llama3|--qwen] <tokenizer file> encode|decode|info\n", argv[0]);
     return 2;
   }
   const std::string mode = argv[2];
-  op::SpeEncodeLayer layer(argv[1], /*has_bos=*/true, /*has_eos=*/false);
+  // has_bos as model.cpp:105-115 constructs them: SentencePiece and Llama-3 prepend BOS, Qwen2 does not
+  std::unique_ptr<op::EncodeLayerBase> owned;
+  if (family == "llama3") owned = std::make_unique<op::BpeEncodeLayer>(argv[1], true, false);
+  else if (family == "qwen") owned = std::make_unique<op::QwenEncodeLayer>(argv[1], false, false);
+  else owned = std::make_unique<op::SpeEncodeLayer>(argv[1], true, false);
+  op::EncodeLayerBase& layer = *owned;
   if (mode == "info") {
     std::printf("vocab %d eos_is_2 %d\n", layer.vocab_size(), layer.is_sentence_ending(2) ? 1 : 0);
     return 0;

@@ -131,3 +131,91 @@ def test_unsupported_or_missing_models_are_fatal(models, tmp_path):
     junk.write_bytes(b"\x00\x01not a protobuf at all" * 10)
     r = subprocess.run([_exe(), str(junk), "info"], capture_output=True, text=True, timeout=60)
     assert r.returncode != 0
+
+
+# ---- byte-level BPE (Llama-3 / Qwen2 tokenizer.json) against the Hugging Face `tokenizers` package ----------
+
+LLAMA3_PAT = (r"(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}{1,3}| ?[^\s\p{L}\p{N}]+[\r\n]*|"
+              r"\s*[\r\n]+|\s+(?!\S)|\s+")
+QWEN_PAT = LLAMA3_PAT.replace(r"\p{N}{1,3}", r"\p{N}")
+SPECIALS = {"llama3": ["<|begin_of_text|>", "<|end_of_text|>", "<|eot_id|>", "<|start_header_id|>"],
+            "qwen": ["<|endoftext|>", "<|im_start|>", "<|im_end|>"]}
+
+
+@pytest.fixture(scope="module")
+def bpe_models(tmp_path_factory):
+    tk = pytest.importorskip("tokenizers")
+    from tokenizers import Regex, Tokenizer, decoders, models as tmodels, pre_tokenizers, trainers
+    d = tmp_path_factory.mktemp("bpe")
+    corpus = [l for l in _corpus() if l.strip()]
+    out = {}
+    for family, pat in (("llama3", LLAMA3_PAT), ("qwen", QWEN_PAT)):
+        tok = Tokenizer(tmodels.BPE(ignore_merges=(family == "llama3")))
+        tok.pre_tokenizer = pre_tokenizers.Sequence([
+            pre_tokenizers.Split(Regex(pat), behavior="isolated", invert=False),
+            pre_tokenizers.ByteLevel(add_prefix_space=False, trim_offsets=True, use_regex=False)])
+        tok.decoder = decoders.ByteLevel()
+        trainer = trainers.BpeTrainer(vocab_size=1200, special_tokens=SPECIALS[family], show_progress=False,
+                                      initial_alphabet=pre_tokenizers.ByteLevel.alphabet())
+        tok.train_from_iterator(corpus, trainer)
+        path = d / f"{family}.json"
+        tok.save(str(path))
+        out[family] = (path, tok)
+    return out
+
+
+def _bpe_sentences(family):
+    s = [x for x in _sentences() if "\n" not in x]
+    s += ["it's DON'T we'Re I'LL they'd you'VE I'm", "12345678 1 22 333 4444 5.5 3,141", "a  b   c    d",
+          "  leading and trailing   ", "line\\n\\nbreaks \\n  indented\\n", "tabs\t\tand\tspaces \t mix",
+          "x+=1; y=[1,2,3] # comment!!", "‘quotes’ “double” …ellipsis — dash", "no_space_before(paren)",
+          "日本語のテキスト123と数字", "Ünïcödé ßtraße ŒUVRE", "emoji 🙂🙂 🚀", " nbsp em space　ideographic",
+          SPECIALS[family][0] + "hello" + SPECIALS[family][1], "text " + SPECIALS[family][-1] + " more text",
+          "<|not_a_special|> <|", "'", "''s", "'S", " '", "a'b'c", "ſ 'ſ"]
+    # fuzz: every class the split pattern distinguishes, in random order ("\\n" stands for a newline)
+    rng = random.Random(23)
+    alphabet = (list("abcXYZéßжщ日本ǅ") + list("0123456789²½٣") + list(".,;:!?()[]{}<>|+-*/=_#@&%$^~`\"") +
+                ["'", "'s", "'T", "'re", "'LL", " ", " ", "  ", "\t", "\r", "\\n", "\\n", "\u00a0", "\u3000", "\u2009",
+                 "🙂", "\u0301"])
+    for _ in range(400):
+        s.append("".join(rng.choice(alphabet) for _ in range(rng.randint(1, 24))))
+    return s
+
+
+@pytest.mark.parametrize("family", ["llama3", "qwen"])
+def test_byte_bpe_matches_hf_tokenizers(bpe_models, family):
+    path, tok = bpe_models[family]
+    sents = _bpe_sentences(family)
+    r = subprocess.run([_exe(), f"--{family}", str(path), "encode"], input="\n".join(sents) + "\n",
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = [[int(t) for t in line.split()] for line in r.stdout.split("\n")[:len(sents)]]
+    bos = [tok.token_to_id("<|begin_of_text|>")] if family == "llama3" else []  # Qwen2: no BOS (model.cpp:111)
+    all_ids = []
+    for s, ids in zip(sents, got):
+        want = bos + tok.encode(s.replace("\\n", "\n"), add_special_tokens=False).ids
+        assert ids == want, (family, s)
+        all_ids.append(want)
+    rng = random.Random(5)
+    cases = [c for c in all_ids if c] + [[i] for i in range(tok.get_vocab_size())]
+    cases += [[rng.randrange(tok.get_vocab_size()) for _ in range(rng.randint(1, 10))] for _ in range(300)]
+    r = subprocess.run([_exe(), f"--{family}", str(path), "decode"],
+                       input="\n".join(" ".join(map(str, c)) for c in cases) + "\n", capture_output=True, text=True,
+                       timeout=120)
+    assert r.returncode == 0, r.stderr
+    for c, line in zip(cases, r.stdout.split("\n")):
+        # raw bytes of the pieces; the Python decoder additionally replaces malformed UTF-8
+        want = tok.decode(c, skip_special_tokens=False)
+        assert bytes.fromhex(line).decode("utf-8", errors="replace") == want, (family, c)
+
+
+def test_byte_bpe_info_and_errors(bpe_models, tmp_path):
+    path, tok = bpe_models["qwen"]
+    r = subprocess.run([_exe(), "--qwen", str(path), "info"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.split()[:2] == ["vocab", str(tok.get_vocab_size())]
+    bad = tmp_path / "bad.json"
+    bad.write_text('{"model": {"type": "Unigram"}}')
+    for p in (bad, tmp_path / "missing.json"):
+        r = subprocess.run([_exe(), "--llama3", str(p), "info"], capture_output=True, text=True, timeout=60)
+        assert r.returncode != 0 and "token model path is not valid" in r.stderr
