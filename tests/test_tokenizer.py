@@ -219,3 +219,17 @@ def test_byte_bpe_info_and_errors(bpe_models, tmp_path):
     for p in (bad, tmp_path / "missing.json"):
         r = subprocess.run([_exe(), "--llama3", str(p), "info"], capture_output=True, text=True, timeout=60)
         assert r.returncode != 0 and "token model path is not valid" in r.stderr
+
+
+@pytest.mark.parametrize("flag,vocab,bos", [(None, 32000, True), ("--llama3", 128256, True), ("--qwen", 151936, False)])
+def test_stand_in_tokenizer_for_synthetic_checkpoints(flag, vocab, bos):
+    """Path "<none>": ids in, "<id>" text out, never a sentence end -- what kuiper_decode and the GPU
+    tests of the C++ model run with (synthetic checkpoints have no tokenizer file)."""
+    base = [_exe()] + ([flag] if flag else []) + ["<none>"]
+    r = subprocess.run(base + ["info"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and r.stdout.split() == ["vocab", str(vocab), "eos_is_2", "0"]
+    r = subprocess.run(base + ["encode"], input="hi there\n", capture_output=True, text=True, timeout=60)
+    ids = [int(t) for t in r.stdout.split()]
+    assert (ids[0] == 1) == bos and len(ids) == len("hi there") + (1 if bos else 0)
+    r = subprocess.run(base + ["decode"], input="5 6 7\n", capture_output=True, text=True, timeout=60)
+    assert bytes.fromhex(r.stdout.strip()).decode() == "<5><6><7>"
