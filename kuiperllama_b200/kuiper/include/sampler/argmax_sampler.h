@@ -1,14 +1,28 @@
+// Token samplers.  The decode path is greedy: ArgmaxSampler returns the index of the largest logit,
+// the lowest index on ties, computed on the device the logits live on (argmax_kernel_cu).
+// sampler/sampler.h forwards here.
 #ifndef KLLM_KUIPER_SAMPLER_ARGMAX_SAMPLER_H_
 #define KLLM_KUIPER_SAMPLER_ARGMAX_SAMPLER_H_
-#include <base/base.h>
+#include <cstddef>
 
-#include "sampler.h"
+#include "base/base.h"
+
 namespace sampler {
-// Greedy: index of the maximum logit, lowest index on ties (reference argmax_sampler.cpp:5-13).
-class ArgmaxSampler : public Sampler {
+class Sampler {
  public:
-  explicit ArgmaxSampler(base::DeviceType device_type) : Sampler(device_type) {}
+  explicit Sampler(base::DeviceType device_type) : device_type_(device_type) {}
+  virtual ~Sampler() = default;
+  // logits: `size` floats on this sampler's device; blocks until the id is known
+  virtual size_t sample(const float* logits, size_t size, void* stream = nullptr) = 0;
+
+ protected:
+  base::DeviceType device_type_;
+};
+
+class ArgmaxSampler final : public Sampler {
+ public:
+  using Sampler::Sampler;
   size_t sample(const float* logits, size_t size, void* stream) override;
 };
 }  // namespace sampler
-#endif
+#endif  // KLLM_KUIPER_SAMPLER_ARGMAX_SAMPLER_H_

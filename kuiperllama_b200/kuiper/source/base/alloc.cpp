@@ -1,6 +1,6 @@
 // Allocators + memcpy/memset helpers (reference alloc.cpp:4-60, alloc_cpu.cpp:13-31,
-// alloc_cu.cpp:7-112 for the behaviour; the pooling strategy is ours, see alloc.h).
-#include "base/alloc.h"
+// alloc_cu.cpp:7-112 for the behaviour; the pooling strategy is ours, see base/memory.h).
+#include "base/memory.h"
 
 #include <cuda_runtime_api.h>
 
@@ -65,7 +65,6 @@ void DeviceAllocator::memset_zero(void* ptr, size_t byte_size, void* stream, boo
 }
 
 // ---- CPU -------------------------------------------------------------------------------------
-CPUDeviceAllocator::CPUDeviceAllocator() : DeviceAllocator(DeviceType::kDeviceCPU) {}
 
 void* CPUDeviceAllocator::allocate(size_t byte_size) const {
   if (byte_size == 0) return nullptr;
@@ -80,7 +79,6 @@ void CPUDeviceAllocator::release(void* ptr) const {
 }
 
 // ---- CUDA ------------------------------------------------------------------------------------
-CUDADeviceAllocator::CUDADeviceAllocator() : DeviceAllocator(DeviceType::kDeviceCUDA) {}
 
 CUDADeviceAllocator::~CUDADeviceAllocator() {
   // process teardown: the driver may already be gone, so errors are ignored on purpose
@@ -147,6 +145,4 @@ size_t CUDADeviceAllocator::cached_bytes() const {
   return cached_;
 }
 
-std::shared_ptr<CPUDeviceAllocator> CPUDeviceAllocatorFactory::instance = nullptr;
-std::shared_ptr<CUDADeviceAllocator> CUDADeviceAllocatorFactory::instance = nullptr;
 }  // namespace base

@@ -1,4 +1,4 @@
-#include "base/buffer.h"
+#include "base/memory.h"
 
 #include <glog/logging.h>
 
@@ -48,12 +48,4 @@ void Buffer::copy_from(const Buffer* buffer) const {
   allocator_->memcpy(buffer->ptr_, ptr_, n, kind_for(buffer->device_type_, device_type_));
 }
 
-void* Buffer::ptr() { return ptr_; }
-const void* Buffer::ptr() const { return ptr_; }
-size_t Buffer::byte_size() const { return byte_size_; }
-std::shared_ptr<DeviceAllocator> Buffer::allocator() const { return allocator_; }
-DeviceType Buffer::device_type() const { return device_type_; }
-void Buffer::set_device_type(DeviceType device_type) { device_type_ = device_type; }
-std::shared_ptr<Buffer> Buffer::get_shared_from_this() { return shared_from_this(); }
-bool Buffer::is_external() const { return use_external_; }
 }  // namespace base

@@ -1,133 +1,164 @@
-// Tokenizer front ends (reference kuiper/source/op/encode.cpp).  See op/encode.h for scope.
+// Encode layers: one shared implementation over a TokenizerBackend (see op/encode.h).
 #include "op/encode.h"
 
-#include <fstream>
 #include <sstream>
+#include <utility>
+
+#include "op/byte_bpe.h"
+#ifdef KLLM_WITH_SENTENCEPIECE
+#include <sentencepiece_processor.h>
+#else
+#include "op/spm_bpe.h"
+#endif
 
 namespace op {
 namespace {
-// "<12><7>" style text for ids: lossless and obviously synthetic
-std::string ids_to_text(const std::vector<int32_t>& ids) {
-  std::ostringstream os;
-  for (int32_t id : ids) os << '<' << id << '>';
-  return os.str();
+[[noreturn]] void refuse(const std::string& path, const std::string& why) {
+  LOG(FATAL) << "The token model path is not valid, please check the path and type of token model: " << path
+             << ": " << why;
+  std::abort();
 }
-// stand-in encoding: BOS (1) then one id per byte, offset past the control ids
-std::vector<int32_t> bytes_to_ids(const std::string& s, bool bos, bool eos, int32_t vocab) {
-  std::vector<int32_t> ids;
-  if (bos) ids.push_back(1);
-  for (unsigned char c : s) ids.push_back(3 + static_cast<int32_t>(c) % (vocab > 259 ? 256 : 1));
-  if (eos) ids.push_back(2);
-  return ids;
-}
+
+// Synthetic checkpoints have no tokenizer file: BOS-free, one id per byte (offset past the control
+// ids) in, "<12><7>" out -- lossless and obviously synthetic.
+class StandInBackend final : public TokenizerBackend {
+ public:
+  explicit StandInBackend(int32_t vocab) : vocab_(vocab) {}
+  std::vector<int32_t> encode(const std::string& text) const override {
+    std::vector<int32_t> ids;
+    for (unsigned char c : text) ids.push_back(3 + static_cast<int32_t>(c) % (vocab_ > 259 ? 256 : 1));
+    return ids;
+  }
+  std::string decode(const std::vector<int32_t>& ids) const override {
+    std::ostringstream os;
+    for (int32_t id : ids) os << '<' << id << '>';
+    return os.str();
+  }
+  int32_t vocab_size() const override { return vocab_; }
+  int32_t id_of(const std::string&) const override { return -1; }
+
+ private:
+  int32_t vocab_;
+};
+
+#ifdef KLLM_WITH_SENTENCEPIECE
+class SentencePieceBackend final : public TokenizerBackend {
+ public:
+  explicit SentencePieceBackend(const std::string& path) {
+    if (!spe_.Load(path).ok()) refuse(path, "libsentencepiece cannot load it");
+  }
+  std::vector<int32_t> encode(const std::string& text) const override { return spe_.EncodeAsIds(text); }
+  std::string decode(const std::vector<int32_t>& ids) const override { return spe_.DecodeIds(ids); }
+  int32_t vocab_size() const override { return spe_.GetPieceSize(); }
+  int32_t id_of(const std::string& tok) const override { return tok == "<s>" ? spe_.bos_id() : tok == "</s>" ? spe_.eos_id() : -1; }
+
+ private:
+  sentencepiece::SentencePieceProcessor spe_;
+};
+#else
+class SpmBackend final : public TokenizerBackend {
+ public:
+  explicit SpmBackend(const std::string& path) {
+    const std::string err = model_.load(path);
+    if (!err.empty()) refuse(path, err);
+  }
+  std::vector<int32_t> encode(const std::string& text) const override { return model_.encode(text); }
+  std::string decode(const std::vector<int32_t>& ids) const override { return model_.decode(ids); }
+  int32_t vocab_size() const override { return model_.piece_size(); }
+  int32_t id_of(const std::string& tok) const override {
+    return tok == "<s>" ? model_.bos_id() : tok == "</s>" ? model_.eos_id() : -1;
+  }
+
+ private:
+  SpmBpeModel model_;
+};
+#endif
+
+class ByteBpeBackend final : public TokenizerBackend {
+ public:
+  explicit ByteBpeBackend(const std::string& path) {
+    const std::string err = model_.load(path);
+    if (!err.empty()) refuse(path, err);
+  }
+  std::vector<int32_t> encode(const std::string& text) const override { return model_.encode(text); }
+  std::string decode(const std::vector<int32_t>& ids) const override { return model_.decode(ids); }
+  int32_t vocab_size() const override { return model_.vocab_size(); }
+  int32_t id_of(const std::string& tok) const override { return model_.token_to_id(tok); }
+
+ private:
+  ByteBpeModel model_;
+};
 }  // namespace
 
+// ---- the shared implementation ------------------------------------------------------------------------------
+EncodeLayerBase::EncodeLayerBase(std::string token_model_path, bool has_bos, bool has_eos)
+    : Layer(base::DeviceType::kDeviceCPU, LayerType::kLayerEncode, "Encode"),
+      has_bos_(has_bos),
+      has_eos_(has_eos),
+      token_model_path_(std::move(token_model_path)) {}
+EncodeLayerBase::~EncodeLayerBase() = default;
+
+void EncodeLayerBase::adopt(std::unique_ptr<TokenizerBackend> backend, int32_t bos_id, int32_t eos_id,
+                            int32_t extra_stop_id, bool stops_generation) {
+  backend_ = std::move(backend);
+  bos_id_ = bos_id, eos_id_ = eos_id, stop_token2_ = extra_stop_id;
+  stops_generation_ = stops_generation;
+}
+
+std::vector<int32_t> EncodeLayerBase::encode(const std::string& sentence) const {
+  CHECK(backend_ != nullptr);
+  std::vector<int32_t> ids = backend_->encode(sentence);
+  if (has_bos_ && bos_id_ >= 0) ids.insert(ids.begin(), bos_id_);
+  if (has_eos_ && eos_id_ >= 0) ids.push_back(eos_id_);
+  return ids;
+}
+std::string EncodeLayerBase::decode(const std::vector<int32_t>& token_ids) const {
+  CHECK(backend_ != nullptr);
+  return backend_->decode(token_ids);
+}
+std::string EncodeLayerBase::decode(int32_t token_id) const { return decode(std::vector<int32_t>{token_id}); }
+bool EncodeLayerBase::is_sentence_ending(int32_t token_id) const {
+  return stops_generation_ && token_id >= 0 && (token_id == eos_id_ || token_id == stop_token2_);
+}
+int32_t EncodeLayerBase::vocab_size() const {
+  CHECK(backend_ != nullptr);
+  return backend_->vocab_size();
+}
+
+// ---- the families -----------------------------------------------------------------------------------------------
 SpeEncodeLayer::SpeEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos)
     : EncodeLayerBase(std::move(token_model_path), has_bos, has_eos) {
-#ifdef KLLM_WITH_SENTENCEPIECE
-  spe = std::make_unique<sentencepiece::SentencePieceProcessor>();
-  auto rc = spe->Load(token_model_path_);
-  if (!rc.ok()) {
-    LOG(FATAL) << "The token model path is not valid, please check the path and type of token model.";
-  }
-#else
-  if (token_model_path_.empty() || token_model_path_ == "<none>") {
+  if (is_stand_in_path(token_model_path_)) {
     LOG(INFO) << "no tokenizer model given: using the id-level stand-in tokenizer";
+    adopt(std::make_unique<StandInBackend>(32000), /*bos=*/1, /*eos=*/2, -1, /*stops_generation=*/false);
     return;
   }
-  spm_ = std::make_unique<SpmBpeModel>();
-  const std::string err = spm_->load(token_model_path_);
-  if (!err.empty()) {
-    LOG(FATAL) << "The token model path is not valid, please check the path and type of token model: "
-               << token_model_path_ << ": " << err;
-  }
-#endif
-}
-
-std::vector<int32_t> SpeEncodeLayer::encode(const std::string& sentence) const {
 #ifdef KLLM_WITH_SENTENCEPIECE
-  std::vector<int32_t> ids = spe->EncodeAsIds(sentence);
-  if (has_bos_) ids.insert(ids.begin(), spe->bos_id());
-  if (has_eos_) ids.push_back(spe->eos_id());
-  return ids;
+  auto backend = std::make_unique<SentencePieceBackend>(token_model_path_);
 #else
-  if (!spm_) return bytes_to_ids(sentence, has_bos_, has_eos_, stub_vocab_);
-  std::vector<int32_t> ids = spm_->encode(sentence);
-  if (has_bos_) ids.insert(ids.begin(), spm_->bos_id());
-  if (has_eos_) ids.push_back(spm_->eos_id());
-  return ids;
+  auto backend = std::make_unique<SpmBackend>(token_model_path_);
 #endif
-}
-
-std::string SpeEncodeLayer::decode(int32_t token_id) const { return decode(std::vector<int32_t>{token_id}); }
-
-std::string SpeEncodeLayer::decode(const std::vector<int32_t>& token_ids) const {
-#ifdef KLLM_WITH_SENTENCEPIECE
-  return spe->DecodeIds(token_ids);
-#else
-  return spm_ ? spm_->decode(token_ids) : ids_to_text(token_ids);
-#endif
-}
-
-bool SpeEncodeLayer::is_sentence_ending(int32_t token_id) const {
-#ifdef KLLM_WITH_SENTENCEPIECE
-  return token_id == spe->eos_id();
-#else
-  // stand-in (synthetic checkpoints): always decode the requested number of steps
-  return spm_ ? token_id == spm_->eos_id() : false;
-#endif
-}
-
-int32_t SpeEncodeLayer::vocab_size() const {
-#ifdef KLLM_WITH_SENTENCEPIECE
-  return spe->GetPieceSize();
-#else
-  return spm_ ? spm_->piece_size() : stub_vocab_;
-#endif
+  const int32_t bos = backend->id_of("<s>"), eos = backend->id_of("</s>");
+  adopt(std::move(backend), bos, eos, -1, true);
 }
 
 BpeEncodeLayer::BpeEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos, const char* bos,
-                               const char* eos, const char* stop2, int32_t stub_vocab)
+                               const char* eos, const char* extra_stop, int32_t stand_in_vocab)
     : EncodeLayerBase(std::move(token_model_path), has_bos, has_eos) {
-  if (token_model_path_.empty() || token_model_path_ == "<none>") {
-    bos_id_ = 1, eos_id_ = 2;
-    num_token_ = stub_vocab;  // overwritten by the checkpoint header (model.cpp)
+  if (is_stand_in_path(token_model_path_)) {
     LOG(INFO) << "no tokenizer.json given: using the id-level stand-in tokenizer";
+    // the vocabulary size is overwritten by the checkpoint header anyway (model.cpp)
+    adopt(std::make_unique<StandInBackend>(stand_in_vocab), 1, 2, -1, false);
     return;
   }
-  bpe_ = std::make_unique<ByteBpeModel>();
-  const std::string err = bpe_->load(token_model_path_);
-  if (!err.empty()) {
-    LOG(FATAL) << "The token model path is not valid, please check the path and type of token model: "
-               << token_model_path_ << ": " << err;
-  }
-  bos_id_ = bpe_->token_to_id(bos);
-  eos_id_ = bpe_->token_to_id(eos);
-  stop_token1_ = eos_id_;
-  stop_token2_ = bpe_->token_to_id(stop2);
-  num_token_ = bpe_->vocab_size();
+  auto backend = std::make_unique<ByteBpeBackend>(token_model_path_);
+  const int32_t b = backend->id_of(bos), e = backend->id_of(eos), x = backend->id_of(extra_stop);
+  adopt(std::move(backend), b, e, x, true);
 }
 
 BpeEncodeLayer::BpeEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos)
     : BpeEncodeLayer(std::move(token_model_path), has_bos, has_eos, "<|begin_of_text|>", "<|end_of_text|>",
                      "<|eot_id|>", 128256) {}
-
-std::vector<int32_t> BpeEncodeLayer::encode(const std::string& sentence) const {
-  if (!bpe_) return bytes_to_ids(sentence, has_bos_, has_eos_, num_token_);
-  std::vector<int32_t> ids = bpe_->encode(sentence);
-  if (has_bos_ && bos_id_ >= 0) ids.insert(ids.begin(), bos_id_);
-  if (has_eos_ && eos_id_ >= 0) ids.push_back(eos_id_);
-  return ids;
-}
-std::string BpeEncodeLayer::decode(int32_t token_id) const { return decode(std::vector<int32_t>{token_id}); }
-std::string BpeEncodeLayer::decode(const std::vector<int32_t>& token_ids) const {
-  return bpe_ ? bpe_->decode(token_ids) : ids_to_text(token_ids);
-}
-bool BpeEncodeLayer::is_sentence_ending(int32_t token_id) const {
-  // stand-in (synthetic checkpoints): always decode the requested number of steps
-  return bpe_ != nullptr && token_id >= 0 && (token_id == stop_token1_ || token_id == stop_token2_);
-}
-int32_t BpeEncodeLayer::vocab_size() const { return num_token_; }
 
 QwenEncodeLayer::QwenEncodeLayer(std::string token_model_path, bool has_bos, bool has_eos)
     : BpeEncodeLayer(std::move(token_model_path), has_bos, has_eos, "<|im_start|>", "<|im_end|>", "<|endoftext|>",

@@ -3,6 +3,8 @@
 
 #include <kllm_b200.h>
 
+#include "sampler/argmax_sampler.h"
+
 namespace kernel {
 namespace {
 #if defined(QWEN2_SUPPORT)
@@ -176,3 +178,10 @@ ScaleSumKernel get_scale_sum_kernel(base::DeviceType) {
   return no_cpu_backend<ScaleSumKernel>("get_scale_sum_kernel");
 }
 }  // namespace kernel
+
+// sampler::ArgmaxSampler (sampler/argmax_sampler.h): greedy sampling runs where the logits are; this
+// library has no host path
+size_t sampler::ArgmaxSampler::sample(const float* logits, size_t size, void* stream) {
+  CHECK(device_type_ == base::DeviceType::kDeviceCUDA) << "ArgmaxSampler: CUDA logits only (no CPU backend)";
+  return kernel::argmax_kernel_cu(logits, size, stream);
+}

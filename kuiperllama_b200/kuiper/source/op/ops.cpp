@@ -131,8 +131,6 @@ MultiHeadAttention::MultiHeadAttention(base::DeviceType device_type, int32_t lay
   reset_input_size(5);
   reset_output_size(1);
 }
-void MultiHeadAttention::set_pos(int32_t pos) { pos_ = pos; }
-void MultiHeadAttention::set_layer_idx(int32_t layer_idx) { layer_index_ = layer_idx; }
 base::Status MultiHeadAttention::check() const {
   for (int32_t i = 0; i < 4; ++i) {  // query, score, key cache, value cache
     base::Status st = check_tensor(get_input(i), device_type_, data_type_);
