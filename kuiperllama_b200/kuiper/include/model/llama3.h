@@ -63,6 +63,7 @@ class LLama2Model : public Model {
               bool is_quant_model, bool qkv_bias);
 
  private:
+  friend struct ModelInspector;
   // Model's loading hooks
   void init_mem() override;
   base::Status create_layers() override;

@@ -60,6 +60,7 @@ class Model {
                                     bool is_prompt) const;
 
  protected:
+  friend struct ModelInspector;  // tools/kuiper_selftest.cpp: drives the loading pipeline without a GPU
   // loading pipeline
   virtual base::Status gen_model_from_file();
   virtual base::Status create_encode_layer();

@@ -3,7 +3,7 @@
 // assign1/clone_cpu; test/test_tensor/test_buffer.cpp: allocate/use_external) plus the Status,
 // layer-check and checkpoint-header behaviour the model code relies on.  Plain asserts, no gtest.
 //
-//   kuiper_selftest [checkpoint.bin]      exit code 0 = all passed
+//   kuiper_selftest [checkpoint.bin [llama|qwen fp32|int8]]      exit code 0 = all passed
 #include <base/base.h>
 #include <base/buffer.h>
 #include <glog/logging.h>
@@ -15,11 +15,27 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "model/config.h"
+#include "model/llama3.h"
+#include "model/qwen2.h"
 #include "model/raw_model_data.h"
+
+namespace model {
+// Runs the loading pipeline of a model (tokenizer stand-in -> mmap + header -> layers as views into
+// the mapping) WITHOUT init(): no GPU involved, nothing uploaded.
+struct ModelInspector {
+  static base::Status load(LLama2Model& m) { return m.gen_model_from_file(); }
+  static const TransformerConfig& config(const LLama2Model& m) { return *m.config_; }
+  static const LLama2Layers& layers(const LLama2Model& m) { return *m.llama_layers_; }
+  static const char* payload(const LLama2Model& m) { return static_cast<const char*>(m.raw_model_data_->weight_data); }
+  static size_t file_size(const LLama2Model& m) { return m.raw_model_data_->file_size; }
+  static int32_t group_size(const LLama2Model& m) { return m.group_size_; }
+};
+}  // namespace model
 
 namespace {
 int g_failed = 0, g_run = 0;
@@ -179,6 +195,99 @@ int main(int argc, char** argv) {
       EXPECT(cfg.dim > 0 && cfg.layer_num > 0 && cfg.head_num % cfg.kv_head_num == 0);
       std::printf("         dim %d hidden %d layers %d heads %d kv_heads %d vocab %d seq_len %d\n", cfg.dim,
                   cfg.hidden_dim, cfg.layer_num, cfg.head_num, cfg.kv_head_num, cfg.vocab_size, cfg.seq_len);
+    });
+  }
+
+  // kuiper_selftest <ckpt> <llama|qwen> <fp32|int8>: the layers must be views at the offsets the
+  // exporter's layout implies (tools/export.py / export_qwen2.py), computed here independently
+  if (argc > 3) {
+    const std::string family = argv[2];
+    const bool quant = std::string(argv[3]) == "int8";
+    run("model loading pipeline: header, config, every weight a view at its file offset", [&] {
+      std::unique_ptr<model::LLama2Model> m;
+      if (family == "qwen")
+        m = std::make_unique<model::Qwen2Model>(TokenizerType::kEncodeBpe, "<none>", argv[1], quant);
+      else
+        m = std::make_unique<model::LLama2Model>(TokenizerType::kEncodeSpe, "<none>", argv[1], quant);
+      using I = model::ModelInspector;
+      const base::Status st = I::load(*m);
+      EXPECT(bool(st));
+      if (!st) return;
+      const auto& c = I::config(*m);
+      const auto& ly = I::layers(*m);
+      const size_t dim = c.dim_, kvd = c.kv_dim_, hid = c.hidden_dim_, L = c.layer_num_, V = c.vocab_size_;
+      EXPECT(c.head_size_ * c.head_num_ == c.dim_ && c.kv_mul_ * c.kv_head_num_ == c.head_num_);
+      EXPECT(ly.wq_layers_.size() == L && ly.w2_layers_.size() == L && ly.rmsnorm_layers_.size() == 2 * L + 1);
+      auto weight_at = [&](const std::shared_ptr<op::Layer>& l) {
+        return reinterpret_cast<const char*>(std::static_pointer_cast<op::LayerParam>(l)->get_weight(0).ptr<int8_t>());
+      };
+      const char* base_ptr = I::payload(*m);
+      const bool bias = family == "qwen" && !quant;
+      if (!quant) {
+        size_t off = 0;  // bytes
+        EXPECT(weight_at(ly.embedding_layer_) == base_ptr + off);
+        off += V * dim * 4;
+        EXPECT(weight_at(ly.rmsnorm_layers_[0]) == base_ptr + off);
+        off += L * dim * 4;
+        const size_t q_stride = (dim * dim + (bias ? dim : 0)) * 4, kv_stride = (kvd * dim + (bias ? kvd : 0)) * 4;
+        EXPECT(weight_at(ly.wq_layers_[L - 1]) == base_ptr + off + (L - 1) * q_stride);
+        off += L * q_stride;
+        EXPECT(weight_at(ly.wk_layers_[L - 1]) == base_ptr + off + (L - 1) * kv_stride);
+        off += L * kv_stride;
+        EXPECT(weight_at(ly.wv_layers_[0]) == base_ptr + off);
+        off += L * kv_stride;
+        EXPECT(weight_at(ly.wo_layers_[0]) == base_ptr + off);
+        off += L * dim * dim * 4;
+        EXPECT(weight_at(ly.rmsnorm_layers_[L]) == base_ptr + off);  // first ffn norm
+        off += L * dim * 4;
+        EXPECT(weight_at(ly.w1_layers_[0]) == base_ptr + off);
+        off += L * hid * dim * 4;
+        EXPECT(weight_at(ly.w2_layers_[0]) == base_ptr + off);
+        off += L * dim * hid * 4;
+        EXPECT(weight_at(ly.w3_layers_[L - 1]) == base_ptr + off + (L - 1) * hid * dim * 4);
+        off += L * hid * dim * 4;
+        EXPECT(weight_at(ly.rmsnorm_layers_[2 * L]) == base_ptr + off);  // final norm
+        off += dim * 4 + static_cast<size_t>(c.seq_len_) * c.head_size_ * 4;  // + freqs_cos | freqs_sin
+        if (c.is_shared_weight_) {
+          EXPECT(weight_at(ly.cls_layer_) == weight_at(ly.embedding_layer_));
+        } else {
+          EXPECT(weight_at(ly.cls_layer_) == base_ptr + off);
+          off += V * dim * 4;
+        }
+        EXPECT(off + 28 == I::file_size(*m));
+        if (bias) {
+          auto mm = std::static_pointer_cast<op::MatmulLayer>(ly.wq_layers_[0]);
+          EXPECT(mm->has_bias());
+          EXPECT(reinterpret_cast<const char*>(mm->get_bias(0).ptr<float>()) == weight_at(ly.wq_layers_[0]) + dim * dim * 4);
+        }
+      } else {
+        const size_t g = static_cast<size_t>(I::group_size(*m));
+        EXPECT(g == 64);
+        auto blob = [&](size_t rows, size_t cols) { return rows * cols + rows * cols / g * 4; };
+        size_t off = 0;
+        EXPECT(weight_at(ly.wq_layers_[0]) == base_ptr + off);
+        auto q0 = std::static_pointer_cast<op::LayerParam>(ly.wq_layers_[0]);
+        EXPECT(reinterpret_cast<const char*>(q0->get_scales().ptr<float>()) == base_ptr + dim * dim);
+        off += L * blob(dim, dim);
+        EXPECT(weight_at(ly.wk_layers_[0]) == base_ptr + off);
+        off += 2 * L * blob(kvd, dim);
+        EXPECT(weight_at(ly.wo_layers_[0]) == base_ptr + off);
+        off += L * blob(dim, dim);
+        EXPECT(weight_at(ly.w1_layers_[0]) == base_ptr + off);
+        off += L * blob(hid, dim);
+        EXPECT(weight_at(ly.w2_layers_[L - 1]) == base_ptr + off + (L - 1) * blob(dim, hid));
+        off += L * blob(dim, hid);
+        EXPECT(weight_at(ly.w3_layers_[0]) == base_ptr + off);
+        off += L * blob(hid, dim);
+        EXPECT(weight_at(ly.cls_layer_) == base_ptr + off);
+        off += blob(V, dim);
+        EXPECT(weight_at(ly.embedding_layer_) == base_ptr + off);
+        off += V * dim * 4;
+        EXPECT(weight_at(ly.rmsnorm_layers_[0]) == base_ptr + off);
+        EXPECT(weight_at(ly.rmsnorm_layers_[2 * L]) == base_ptr + off + 2 * L * dim * 4);
+        off += (2 * L + 1) * dim * 4;
+        EXPECT(off + 32 == I::file_size(*m));
+      }
     });
   }
 

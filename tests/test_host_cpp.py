@@ -64,6 +64,21 @@ def test_host_api_selftest_cpu_cases(kllm_lib):
     assert "0 failed expectation(s)" in r.stdout and "FAILED" not in r.stdout
 
 
+@pytest.mark.parametrize("name,family,prec", [("tiny_llama2_fp32", "llama", "fp32"),
+                                              ("tiny_llama2_fp32_shared", "llama", "fp32"),
+                                              ("tiny_llama2_int8", "llama", "int8"),
+                                              ("tiny_qwen2file_fp32", "qwen", "fp32")])
+def test_host_loading_pipeline_without_a_gpu(kllm_lib, name, family, prec):
+    """Model::gen_model_from_file on the golden checkpoints (no init(), no GPU): header -> config, and
+    every layer's weight / scale / bias is a view into the mapping at the offset the exporter's
+    layout implies (computed independently inside kuiper_selftest)."""
+    out = build_host.build("llama2")
+    r = subprocess.run([str(out / "kuiper_selftest"), str(GOLDEN / f"{name}.bin"), family, prec],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "[  ok  ] model loading pipeline" in r.stdout and "0 failed expectation(s)" in r.stdout
+
+
 def test_host_fails_loudly_without_a_gpu(kllm_lib):
     import torch
     if torch.cuda.is_available():
