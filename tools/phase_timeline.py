@@ -49,16 +49,13 @@ def main():
     idx = [P - 1]
     print(f"{'cls':>10} {1:5d} {dur[idx].mean():9.2f} {np.median(stage[:, idx]):8.2f} {np.median(work[:, idx]):9.2f} "
           f"{work[:, idx].max(axis=0).mean():9.2f} {bar[:, idx].min(axis=0).mean():11.2f} {np.median(bar[:, idx]):11.2f}")
-    # how far ahead of the consumers the producer finishes issuing each phase's copies
-    lead = st[:, :, 0] - st[:, :, 5]
-    gem = [i for i in range(P) if i % 5 != 1 or i == P - 1]
-    print(f"# producer lead (consumer enters phase - producer finished issuing it), us: "
-          + " ".join(f"{nm}={np.median(lead[40:, [l * 5 + k for l in range(1, L)]]):.2f}" for k, nm in enumerate(names) if k != 1))
+    # with tagged hand-overs most phases have no barrier: `barrier_*` is then ~0 and the wait for the
+    # previous phase's outputs shows up in `stage_x` of the consuming phase (the poll loop)
+    heads = shape.head_num
     ai = [l * 5 + 1 for l in range(L)]
-    sa = st[:, ai, :]
-    print("# attention (us): step A scores, median over CTAs %.2f / max %.2f | step B CTAs: flag wait + softmax %.2f | values %.2f" % (
-        np.median(sa[:, :, 1] - sa[:, :, 0]), (sa[:, :, 1] - sa[:, :, 0]).max(axis=0).mean(),
-        (sa[:, :, 7] - sa[:, :, 1]).max(axis=0).mean(), (sa[:, :, 2] - sa[:, :, 7]).max(axis=0).mean()))
+    attn = (st[:heads, ai, 2] - st[:heads, ai, 0])
+    print(f"# attention on the {heads} head CTAs: median {np.median(attn):.2f} us, slowest head per layer (mean) "
+          f"{attn.max(axis=0).mean():.2f} us")
     print(f"# sum of phase durations: {dur.sum():.1f} us; barrier_min = time the LAST arriving CTA spends in the barrier")
 
 
