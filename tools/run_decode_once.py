@@ -1,6 +1,14 @@
 #!/usr/bin/env python
 """Tiny driver for ncu captures: build the decoder for a workload and run a few positions.
-    ncu --set full --import-source on -k regex:decode_megakernel -c 1 -o gpurun_out/mega python tools/run_decode_once.py --steps 8 --start 256
+
+The persistent engine decodes `--start` positions in launch #1 (unprofiled context build-up) and
+`--steps` positions in launch #2; capture the SECOND launch, it is short and sits at the context
+length you asked for (ncu replays a kernel ~40 times, so keep --steps small):
+
+    ncu --set full --clock-control none --import-source on -k regex:decode_megakernel \
+        --launch-skip 1 -c 1 -o gpurun_out/mega python tools/run_decode_once.py --steps 8 --start 504
+
+(without --launch-skip the capture is launch #1: --start tokens, bytes per token = total / start.)
 """
 import argparse
 import sys
