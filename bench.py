@@ -40,6 +40,14 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 METRIC = "decode_tokens_per_s"
+# the one number the reference publishes for this metric -- TinyLlama-1.1B fp32,
+# batch 1, its CUDA backend on an RTX 3060 Laptop GPU (readme.md:25).  Other workloads: none.
+PUBLISHED_TOK_S = {"tinyllama-1.1b": 60.34}
+
+
+def vs_baseline(workload, tok_s):
+    ref = PUBLISHED_TOK_S.get(workload)
+    return tok_s / ref if ref else None
 WORKLOAD_NAMES = {
     "tinyllama-1.1b": "TinyLlama-1.1B fp32 greedy decode, batch 1 (BASELINE.json configs[1])",
     "llama2-7b-int8": "Llama-2-7B int8 g64 (export.py --version 3) greedy decode, batch 1 (configs[2])",
@@ -225,7 +233,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "tokens/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32" if shape.group_size == 0 else "int8w/f32",
+        "vs_baseline": vs_baseline(args.workload, res["value"]),
+        "dtype": "f32" if shape.group_size == 0 else "int8w/f32",
         "data": "synthetic random-init weights (tools/model.py init), greedy decode from token 1",
         "config": {"workload": WORKLOAD_NAMES[args.workload], "shape": shape.name},
         "cpu_baseline": res,
@@ -343,7 +352,7 @@ def run_ours(args, rank, world):
     line = {
         "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None,  # BASELINE.md's only number (60.34 tok/s) is an RTX 3060 Laptop run
+        "vs_baseline": vs_baseline(args.workload, tok_s),  # vs 60.34 tok/s (reference CUDA, RTX 3060 Laptop)
         "dtype": "f32" if shape.group_size == 0 else "int8w/f32",
         "data": "synthetic random-init weights (tools/model.py init, seed %d), greedy decode from token 1" % args.seed,
         "config": {"workload": WORKLOAD_NAMES[args.workload], "shape": shape.name,
