@@ -227,3 +227,65 @@ def test_checker_catches_a_single_slot_exchange():
 def test_checker_catches_a_single_residual_buffer():
     """With ONE residual buffer a CTA that finished staging overwrites x_old under a slower one."""
     _must_fail(Config(world=1, ctas=5, heads=2, kv_heads=1, x_bufs=1), "a single residual buffer")
+
+
+# ---- the graph engine's one-shot all-reduce (csrc/tp_comm.cu allreduce_oneshot_kernel) --------------------
+
+def _oneshot_rank(world, r, mem, flags, calls, slots):
+    """Call n: store my vector into every rank's slot (n % slots) row r, then publish flag n there
+    (the kernel: plain stores, __threadfence_system, st.release.sys); wait for every rank's flag n in my
+    own memory; read all rows.  No other synchronisation between calls."""
+    for n in range(1, calls + 1):
+        s = n % slots
+        for k in range(1, world + 1):
+            dst = (r + k) % world
+            for i in range(3):
+                yield "store"
+                mem[dst][s][r][i] = (n, r, i)
+            yield "store"
+            flags[dst][s][r] = n
+        for src in range(world):
+            while True:
+                yield "load"
+                f = flags[r][s][src]
+                if f == n:
+                    break
+                if f > n:
+                    raise ProtocolError(f"rank {r}: flag of rank {src} is already {f} while waiting for call {n}")
+        for src in range(world):
+            for i in range(3):
+                yield "load"
+                if mem[r][s][src][i] != (n, src, i):
+                    raise ProtocolError(f"rank {r} call {n}: row of rank {src} holds {mem[r][s][src][i]}")
+
+
+def _run_oneshot(world, slots, seed, bias):
+    rng = random.Random(seed)
+    mem = [[[[None] * 3 for _ in range(world)] for _ in range(slots)] for _ in range(world)]
+    flags = [[[0] * world for _ in range(slots)] for _ in range(world)]
+    procs = {r: _oneshot_rank(world, r, mem, flags, 12, slots) for r in range(world)}
+    fast = rng.randrange(world)
+    steps = 0
+    while procs:
+        r = fast if (fast in procs and rng.random() < bias) else rng.choice(list(procs))
+        try:
+            next(procs[r])
+        except StopIteration:
+            del procs[r]
+        steps += 1
+        assert steps < 2_000_000, "deadlock"
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_oneshot_allreduce_slots_and_flags(world):
+    for seed in range(20):
+        for bias in (0.0, 0.9, 0.99):
+            _run_oneshot(world, 2, seed, bias)
+    caught = 0
+    for seed in range(20):
+        for bias in (0.0, 0.9, 0.99):
+            try:
+                _run_oneshot(world, 1, seed, bias)  # one slot: the next call's stores land under a reader
+            except ProtocolError:
+                caught += 1
+    assert caught > 0
