@@ -1,4 +1,5 @@
 """The C++ host side (kuiperllama_b200/kuiper): the reference's kuiper:: API over libkllm_b200.
+(File name: sorts after the kernel / decoder suites, whose parity results it builds on.)
 
 not gpu: it builds with CMake, the reference's demo/main.cpp and demo/main_qwen.cpp compile and
          link against it UNCHANGED (when /root/reference is present), and it fails loudly without
