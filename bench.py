@@ -292,6 +292,7 @@ def run_ours(args, rank, world):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") -------------------------------------------
+    barrier()  # tensor parallel: every rank's kernel waits for its peers' partial sums, so start together
     dec.generate(1, 0, max(W, 3))  # warm-up positions (untimed)
     barrier()
     sampler = ClockSampler(local_rank).start() if rank == 0 else None

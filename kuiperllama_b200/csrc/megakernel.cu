@@ -134,7 +134,7 @@ __device__ __forceinline__ float poll_tagged(const unsigned long long* p, unsign
     const long long t0 = clock64();
     do {
       w = ld_tagged_gpu(p);
-      if (clock64() - t0 > 8000000000LL) {
+      if (clock64() - t0 > 120000000000LL) {
         printf("kllm mega: cta %d thread %d timed out on hand-off tag %u\n", blockIdx.x, threadIdx.x, tag);
         __trap();
       }
@@ -829,7 +829,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
                          static_cast<unsigned>(w[1][k][1] >> 32) == tag;
                 }
               }
-              if (!ok && clock64() - t_start > 8000000000LL) {
+              if (!ok && clock64() - t_start > 120000000000LL) {
                 printf("kllm mega: rank %d cta %d timed out on exchange tag %u from ranks %d..%d\n", P.tp_rank, cta,
                        tag, r0, r0 + (two ? 1 : 0));
                 __trap();
@@ -883,7 +883,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
               if (pr < pairs)
                 ok = ok && static_cast<unsigned>(w[k][0] >> 32) == tag && static_cast<unsigned>(w[k][1] >> 32) == tag;
             }
-            if (!ok && clock64() - t_start > 8000000000LL) {
+            if (!ok && clock64() - t_start > 120000000000LL) {
               printf("kllm mega: cta %d timed out on hand-off tag %u (phase input)\n", cta, tag);
               __trap();
             }

@@ -103,7 +103,7 @@ allreduce_oneshot_kernel(PeerTable peers, int rank, int world, const float* __re
     const uint32_t* mine = peers.flags[rank] + slot * kFlagStride + threadIdx.x;
     const long long t0 = clock64();
     while (ld_acquire_sys(mine) != seq) {
-      if (clock64() - t0 > 8000000000LL) {  // ~4 s: a peer died; fail the launch instead of hanging
+      if (clock64() - t0 > 120000000000LL) {  // ~1 min: a peer died; fail the launch instead of hanging
         printf("kllm tp: rank %d timed out waiting for rank %d (call %u)\n", rank, threadIdx.x, seq);
         __trap();
       }

@@ -188,6 +188,7 @@ def _decoder_rank(rank, world, key, backend, engine, steps, out_dir):
         comm.close()
         return
     assert dec.engine == engine
+    torch.distributed.barrier()  # the ranks' kernels wait for each other's partial sums: start together
     ids = dec.generate(1, 0, steps)
     logits = dec.logits()
     # the host-buffer path walks the same sequence
