@@ -227,11 +227,12 @@ int kllm_decoder_launches_per_step(const kllm_decoder* dec);
  * ring; "graph": CUDA-graph chain of fused launches (shapes the ring does not handle, tensor
  * parallel).  Environment KLLM_ENGINE=graph|persistent forces a choice at create time. */
 const char* kllm_decoder_engine(const kllm_decoder* dec);
-/* Persistent engine only: run n_steps positions and record, for step `profiled_step`, eight
- * globaltimer stamps (ns) per CTA per schedule phase into stamps_host[grid][phases][8]
- * (capacity in uint64 elements): [0] phase entered, [1] input vector staged, [2] last ring stage
- * consumed, [3] grid barrier passed (consumer side); [4] producer warp starts / [5] finishes
- * issuing the phase's TMA copies; [6],[7] unused.  Measurement aid (profiles/). */
+/* Persistent engine only: run n_steps positions and record, for step `profiled_step`, sixteen
+ * stamps per CTA per schedule phase into stamps_host[grid][phases][16] (capacity in uint64
+ * elements).  Globaltimer ns: [0] phase entered, [1] input vector staged (+normalised), [2] last
+ * ring stage consumed, [3] grid barrier passed, [10] input vector polled (before the norm).
+ * SM cycles of warp 0: [4] addend prefetch, [5] dot products, [6] reductions, [7] epilogues,
+ * [8] waiting for ring stages, [9] rows of a stage.  Measurement aid (profiles/). */
 int kllm_decoder_profile(kllm_decoder* dec, int32_t first_token, int32_t start_pos,
                          int32_t n_steps, int32_t profiled_step, uint64_t* stamps_host,
                          int32_t capacity, int32_t* grid_out, int32_t* phases_out);

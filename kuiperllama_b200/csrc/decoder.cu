@@ -484,7 +484,7 @@ int kllm_decoder_profile(kllm_decoder* dc, int32_t first_token, int32_t start_po
   if (!dc->use_mega) return KLLM_E_UNSUPPORTED;
   if (start_pos < 0 || start_pos + n_steps > dc->d.seq_len) return KLLM_E_INVALID;
   const int grid = dc->mega.grid(), phases = dc->mega.phases();
-  const size_t n = static_cast<size_t>(grid) * phases * 8;
+  const size_t n = static_cast<size_t>(grid) * phases * mega::kProfStamps;
   *grid_out = grid;
   *phases_out = phases;
   if (static_cast<size_t>(capacity) < n) return KLLM_E_INVALID;

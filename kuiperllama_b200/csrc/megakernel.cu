@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
         }
         const Phase& ph = s_phase_prod;
         unsigned long long* pstamp = (P.prof != nullptr && tok == P.prof_token && lane == 0)
-                                         ? P.prof + (static_cast<size_t>(cta) * P.n_phases + pi) * 8
+                                         ? P.prof + (static_cast<size_t>(cta) * P.n_phases + pi) * kProfStamps
                                          : nullptr;
         (void)pstamp;
         if (ph.kind == kPhaseAttention) {
@@ -761,7 +761,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
       }
       const Phase& ph = s_phase_cons;
       unsigned long long* stamp =
-          prof_on ? P.prof + (static_cast<size_t>(cta) * P.n_phases + pi) * 8 : nullptr;
+          prof_on ? P.prof + (static_cast<size_t>(cta) * P.n_phases + pi) * kProfStamps : nullptr;
       if (stamp) stamp[0] = global_ns();
 
       if (ph.kind == kPhaseAttention) {
@@ -920,6 +920,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
           for (int i = tid; i < n4; i += kConsumerThreads) xs4w[i] = __ldcg(xg4 + i);
           consumer_sync();
         }
+        if (stamp) stamp[10] = global_ns();
         if (ph.norm_w != nullptr) {
           if (warp == 0) {
             const float sc = rms_scale_smem(xs, M, ph.norm_eps, lane);
@@ -1126,7 +1127,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
         stamp[5] = static_cast<unsigned long long>(cyc4[1]);
         stamp[6] = static_cast<unsigned long long>(cyc4[2]);
         stamp[7] = static_cast<unsigned long long>(cyc4[3]);
-        (void)cyc_wait, (void)cyc_rows;
+        stamp[8] = static_cast<unsigned long long>(cyc_wait);
+        stamp[9] = static_cast<unsigned long long>(cyc_rows);
       }
       if (ph.barrier_after) grid_barrier(P.barrier, bar_target, G);
       if (stamp) stamp[3] = global_ns();

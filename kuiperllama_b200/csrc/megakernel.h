@@ -9,6 +9,7 @@ namespace kllm {
 namespace mega {
 
 enum { kPhaseGemv = 0, kPhaseAttention = 1 };
+constexpr int kProfStamps = 16;  // uint64 stamps per (CTA, phase) of kllm_decoder_profile
 
 struct Seg {
   const void* w;        // fp32 or int8 [rows, in_dim]

@@ -80,6 +80,8 @@ class Oracle:
         L.ko_set_matmul_mode.argtypes = [c_int]
         L.ko_set_blas_library.argtypes = [c_char_p]
         L.ko_num_threads.restype = c_int
+        L.ko_set_num_threads.restype = c_int
+        L.ko_set_num_threads.argtypes = [c_int]
         L.ko_model_open.restype = c_void_p
         L.ko_model_open.argtypes = [c_char_p, c_int, c_int]
         L.ko_model_close.argtypes = [c_void_p]
@@ -193,12 +195,19 @@ class Oracle:
 
     def use_fast_matmul(self, on=True, blas=None):
         """Timed-baseline mode only: OpenBLAS sgemv (what Armadillo calls) or OpenMP rows."""
+        self.blas_loaded = False
         if on and blas:
-            self.L.ko_set_blas_library(str(blas).encode())
+            self.blas_loaded = self.L.ko_set_blas_library(str(blas).encode()) == 0
         self.L.ko_set_matmul_mode(1 if on else 0)
+        return self.blas_loaded
 
     def num_threads(self):
         return int(self.L.ko_num_threads())
+
+    def set_num_threads(self, n):
+        """OpenMP and the loaded BLAS through their own APIs (survives OMP_NUM_THREADS=1 in the
+        environment); returns the thread count the BLAS reports (0: no BLAS loaded)."""
+        return int(self.L.ko_set_num_threads(int(n)))
 
 
 class OracleModel:
@@ -227,15 +236,21 @@ class OracleModel:
 
 def find_openblas():
     """A BLAS with cblas_sgemv for the TIMED cpu baseline (the reference's Armadillo would
-    call OpenBLAS sgemv).  Bundled in wheels in this image; None if absent."""
+    call OpenBLAS sgemv).  Bundled in wheels in this image; every candidate is dlopen-ed and
+    checked for the symbol (a wheel-bundled library may miss its own dependencies); None if
+    nothing usable is found."""
     import glob
     import site
-    pats = ["opencv_python_headless.libs/libopenblas*.so*", "scipy.libs/libscipy_openblas-*.so*"]
+    pats = ["scipy.libs/libscipy_openblas-*.so*", "opencv_python_headless.libs/libopenblas*.so*"]
     for sp in site.getsitepackages():
         for pat in pats:
-            hits = sorted(glob.glob(os.path.join(sp, pat)))
-            if hits:
-                return hits[0]
+            for hit in sorted(glob.glob(os.path.join(sp, pat))):
+                try:
+                    lib = ctypes.CDLL(hit, mode=ctypes.RTLD_LOCAL)
+                except OSError:
+                    continue
+                if hasattr(lib, "cblas_sgemv") or hasattr(lib, "scipy_cblas_sgemv"):
+                    return hit
     return None
 
 

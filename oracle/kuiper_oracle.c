@@ -26,6 +26,7 @@ static int g_matmul_mode = KO_MATMUL_STRICT;
 typedef void (*cblas_sgemv_fn)(int order, int trans, int m, int n, float alpha, const float* a,
                                int lda, const float* x, int incx, float beta, float* y, int incy);
 static cblas_sgemv_fn g_sgemv = NULL;
+static void* g_blas_handle = NULL;
 
 void ko_set_matmul_mode(int mode) { g_matmul_mode = mode; }
 
@@ -36,7 +37,27 @@ int ko_set_blas_library(const char* so) {
   if (!f) f = dlsym(h, "scipy_cblas_sgemv");
   if (!f) return -2;
   g_sgemv = (cblas_sgemv_fn)f;
+  g_blas_handle = h;
   return 0;
+}
+
+/* Thread count of the TIMED baseline, set through the libraries' own APIs so that an inherited
+ * OMP_NUM_THREADS=1 (torchrun exports it) cannot silently serialise the reference arm.  Returns
+ * what the BLAS reports afterwards (0: no BLAS loaded). */
+int ko_set_num_threads(int n) {
+  if (n < 1) n = 1;
+#ifdef _OPENMP
+  omp_set_num_threads(n);
+#endif
+  if (!g_blas_handle) return 0;
+  typedef void (*set_fn)(int);
+  typedef int (*get_fn)(void);
+  set_fn set = (set_fn)dlsym(g_blas_handle, "openblas_set_num_threads");
+  if (!set) set = (set_fn)dlsym(g_blas_handle, "scipy_openblas_set_num_threads");
+  if (set) set(n);
+  get_fn get = (get_fn)dlsym(g_blas_handle, "openblas_get_num_threads");
+  if (!get) get = (get_fn)dlsym(g_blas_handle, "scipy_openblas_get_num_threads");
+  return get ? get() : 0;
 }
 
 int ko_num_threads(void) {

@@ -39,6 +39,7 @@ enum { KO_MATMUL_STRICT = 0, KO_MATMUL_FAST = 1 };
 void ko_set_matmul_mode(int mode);       /* default KO_MATMUL_STRICT */
 int ko_set_blas_library(const char* so); /* dlopen an OpenBLAS for KO_MATMUL_FAST; 0 = ok */
 int ko_num_threads(void);                /* threads KO_MATMUL_FAST will use */
+int ko_set_num_threads(int n);           /* OpenMP + loaded BLAS, via their APIs; returns the BLAS's count (0: none) */
 
 float ko_flavour_eps(int flavour);   /* rmsnorm_kernel.cpp:20-24 */
 float ko_flavour_theta(int flavour); /* rope_kernel.cpp:8,48,88 */

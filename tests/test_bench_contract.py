@@ -44,3 +44,30 @@ def test_product_arm_needs_cuda():
         pytest.skip("a GPU is present")
     r = _run("--workload", "stories15m", "--steps", "4", "--warmup", "3", "--no-cpu-baseline")
     assert r.returncode != 0 and r.stdout.strip() == ""
+
+
+def test_timed_positions_cover_the_metrics_context():
+    """--steps is the number of timed positions, not the context: fewer than 1024 steps are spread
+    as equal windows over context 1 -> 1024; 1024 or more run the whole context in one window."""
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert bench.plan_windows(1024, 1024) == [(0, 1024)]
+    for steps in (1, 3, 4, 20, 64, 100, 1000):
+        w = bench.plan_windows(steps, 1024)
+        assert sum(n for _, n in w) == steps and len(w) <= 16
+        assert all(0 <= s and s + n <= 1024 for s, n in w)
+        assert all(w[i][0] + w[i][1] <= w[i + 1][0] for i in range(len(w) - 1))  # disjoint, ordered
+        if len(w) > 1:
+            assert w[0][0] == 0 and w[-1][0] + w[-1][1] == 1024  # from context 1 to context 1024
+            mean_pos = sum(s + (n - 1) / 2 for s, n in w) / len(w)
+            assert abs(mean_pos - 511.5) < 40
+    assert bench.plan_windows(20, 1024) == [(0, 4), (255, 4), (510, 4), (765, 4), (1020, 4)]
+
+
+def test_default_workload_follows_the_metric():
+    sys.path.insert(0, str(ROOT))
+    import bench
+    assert bench.default_workload(2) == bench.default_workload(8) == "llama2-7b-int8"
+    import torch
+    if not torch.cuda.is_available():
+        assert bench.default_workload(1) == "tinyllama-1.1b"

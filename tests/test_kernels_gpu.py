@@ -178,7 +178,8 @@ def test_rope(kllm_lib, ref, ref_qwen, oracle, flavour, dim, kv_dim, head_size):
 # ---- attention ------------------------------------------------------------------------------------
 @pytest.mark.parametrize("heads,kv_heads,head_size,seq_len,positions", [
     (6, 6, 48, 256, [0, 1, 5, 255]), (32, 4, 64, 2048, [0, 31, 32, 33, 300, 1023, 2047]),
-    (14, 2, 64, 512, [0, 257, 511]), (32, 32, 128, 1024, [0, 100, 1023])])
+    (14, 2, 64, 512, [0, 257, 511]), (32, 32, 128, 1024, [0, 100, 1023]),
+    (14, 2, 64, 4096, [0, 1023, 4095])])  # Qwen2.5-0.5B geometry (kv_mul 7) to pos 1023 and beyond
 def test_mha_decode(kllm_lib, ref, oracle, heads, kv_heads, head_size, seq_len, positions):
     kv_dim = kv_heads * head_size; kv_mul = heads // kv_heads; L = 2; layer = 1
     kc = rnd((L, seq_len, kv_dim), 11); vc = rnd((L, seq_len, kv_dim), 12)

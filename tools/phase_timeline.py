@@ -23,16 +23,21 @@ def main():
     dec = Decoder(shape, synth_weights(shape, "cuda", 1235))
     assert dec.engine == "persistent"
     dec.generate(1, 0, 8)
-    cap = 200 * 2000 * 8
+    NS = 16  # stamps per (CTA, phase): mega::kProfStamps
+    cap = 200 * 2000 * NS
     buf = np.zeros(cap, np.uint64)
     g, p = ctypes.c_int32(), ctypes.c_int32()
     n = a.pos + 1
     check(dec.lib.kllm_decoder_profile(dec.handle, 1, 0, n, a.pos, buf.ctypes.data_as(ctypes.c_void_p), cap,
                                        ctypes.byref(g), ctypes.byref(p)), "profile")
     G, P = g.value, p.value
-    st = buf[: G * P * 8].reshape(G, P, 8).astype(np.int64)
+    raw = buf[: G * P * NS].reshape(G, P, NS).astype(np.int64)
+    st = raw[:, :, :4]
+    cyc = raw[:, :, 4:10]  # SM cycles of warp 0: addend prefetch, dots, reductions, epilogues, ring waits, stage rows
+    polled = raw[:, :, 10]
     t0 = st[:, 0, 0].min()
     st = (st - t0) / 1e3  # us
+    polled = np.where(polled > 0, (polled - t0) / 1e3, st[:, :, 1])
     L = shape.layer_num
     print(f"# {shape.name}: phase timeline of the decode step at pos {a.pos} (us, globaltimer), grid {G}, {P} phases")
     print(f"# token time (first phase entered -> last barrier passed): {st[:, -1, 3].max():.1f} us")
@@ -41,14 +46,19 @@ def main():
     work = (st[:, :, 2] - st[:, :, 1])           # consuming ring stages (or attention)
     bar = (st[:, :, 3] - st[:, :, 2])            # waiting at the grid barrier
     dur = st[:, :, 3].max(axis=0) - st[:, :, 0].min(axis=0)
-    print(f"{'phase':>10} {'count':>5} {'phase_us':>9} {'stage_x':>8} {'work_med':>9} {'work_max':>9} {'barrier_min':>11} {'barrier_med':>11}")
+    poll = polled - st[:, :, 0]                  # of stage_x: until the input vector is complete
+    ghz = 1.965  # cycles -> us at the B200's boost clock (clocks.max.sm); the split is what matters
+    print(f"{'phase':>10} {'count':>5} {'phase_us':>9} {'stage_x':>8} {'(poll)':>7} {'work_med':>9} {'work_max':>9} {'barrier_min':>11} "
+          f"{'barrier_med':>11} | warp 0 of the median CTA, us: {'ringwait':>8} {'dots':>6} {'reduce':>6} {'epilog':>6} {'addend':>6}")
+
+    def row(nm, idx):
+        c = np.median(cyc[:, idx], axis=0).mean(axis=0) / ghz / 1e3 if len(idx) > 1 else np.median(cyc[:, idx], axis=0)[0] / ghz / 1e3
+        print(f"{nm:>10} {len(idx):5d} {dur[idx].mean():9.2f} {np.median(stage[:, idx]):8.2f} {np.median(poll[:, idx]):7.2f} {np.median(work[:, idx]):9.2f} "
+              f"{work[:, idx].max(axis=0).mean():9.2f} {bar[:, idx].min(axis=0).mean():11.2f} {np.median(bar[:, idx]):11.2f} | "
+              f"{'':32s}{c[4]:8.2f} {c[1]:6.2f} {c[2]:6.2f} {c[3]:6.2f} {c[0]:6.2f}")
     for k, nm in enumerate(names):
-        idx = [l * 5 + k for l in range(L)]
-        print(f"{nm:>10} {len(idx):5d} {dur[idx].mean():9.2f} {np.median(stage[:, idx]):8.2f} {np.median(work[:, idx]):9.2f} "
-              f"{work[:, idx].max(axis=0).mean():9.2f} {bar[:, idx].min(axis=0).mean():11.2f} {np.median(bar[:, idx]):11.2f}")
-    idx = [P - 1]
-    print(f"{'cls':>10} {1:5d} {dur[idx].mean():9.2f} {np.median(stage[:, idx]):8.2f} {np.median(work[:, idx]):9.2f} "
-          f"{work[:, idx].max(axis=0).mean():9.2f} {bar[:, idx].min(axis=0).mean():11.2f} {np.median(bar[:, idx]):11.2f}")
+        row(nm, [l * 5 + k for l in range(L)])
+    row("cls", [P - 1])
     # with tagged hand-overs most phases have no barrier: `barrier_*` is then ~0 and the wait for the
     # previous phase's outputs shows up in `stage_x` of the consuming phase (the poll loop)
     heads = shape.head_num
