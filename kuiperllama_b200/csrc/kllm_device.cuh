@@ -80,6 +80,43 @@ __device__ __forceinline__ float block128_sum_quad(const float acc[4]) {
   return __fadd_rn(__fadd_rn(__fadd_rn(v0, a1), a2), a3);
 }
 
+// The two reductions above, "packed": only lane 0's value of the cub tree is ever used, and that
+// value is the balanced binary tree over the 32 lanes (adjacent pairs first), so lanes may trade
+// accumulators instead of all reducing all four: after the offset-1 step every lane carries two of
+// the four virtual warps, after offset 2 one.  Every addition has the same two operands as in
+// cub's tree (FADD commutes), so the result is bit-identical; 10 shuffles + 9 adds instead of
+// 20 + 23.  The total is returned in EVERY lane.
+__device__ __forceinline__ float block128_sum_vt_packed(const float acc[4], int lane) {
+  const bool odd = lane & 1;
+  // offset 1: even lanes keep virtual warps 0,1 -- odd lanes 2,3
+  const float k0 = odd ? acc[2] : acc[0], k1 = odd ? acc[3] : acc[1];
+  const float g0 = odd ? acc[0] : acc[2], g1 = odd ? acc[1] : acc[3];
+  const float s0 = __fadd_rn(k0, __shfl_xor_sync(kFull, g0, 1));
+  const float s1 = __fadd_rn(k1, __shfl_xor_sync(kFull, g1, 1));
+  // offset 2: bit 1 of the lane picks which of the two survives
+  const bool hi = lane & 2;
+  float v = __fadd_rn(hi ? s1 : s0, __shfl_xor_sync(kFull, hi ? s0 : s1, 2));
+  v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 4));
+  v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 8));
+  v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 16));
+  // lanes == 0,2,1,3 (mod 4) now hold virtual warps 0,1,2,3
+  const float a0 = __shfl_sync(kFull, v, 0), a1 = __shfl_sync(kFull, v, 2);
+  const float a2 = __shfl_sync(kFull, v, 1), a3 = __shfl_sync(kFull, v, 3);
+  return __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+}
+
+// acc[e] = virtual thread (4*lane + e): offsets 1 and 2 of the tree are lane-local, offsets 4, 8,
+// 16 are lane distances 1, 2, 4 inside each group of 8 lanes (= one virtual warp).
+__device__ __forceinline__ float block128_sum_quad_packed(const float acc[4]) {
+  float v = __fadd_rn(__fadd_rn(acc[0], acc[1]), __fadd_rn(acc[2], acc[3]));
+  v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 1));
+  v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 2));
+  v = __fadd_rn(v, __shfl_xor_sync(kFull, v, 4));
+  const float a0 = __shfl_sync(kFull, v, 0), a1 = __shfl_sync(kFull, v, 8);
+  const float a2 = __shfl_sync(kFull, v, 16), a3 = __shfl_sync(kFull, v, 24);
+  return __fadd_rn(__fadd_rn(__fadd_rn(a0, a1), a2), a3);
+}
+
 // Exact int8 -> fp32 for the four bytes of `packed` without the slow I2F pipe:
 // (b ^ 0x80) dropped into the mantissa of 2^23 gives 2^23 + b + 128; subtracting
 // 2^23 + 128 is exact.  Equal to static_cast<float>(int8) (matmul_kernel.cu:73).

@@ -16,13 +16,21 @@
 // classifier + greedy argmax.  RoPE moves into the attention phase so GEMV rows can be split
 // evenly over all SMs.
 //
+// Consumers (CW warps: 8 for fp32 weights, 16 for int8): the rows of a ring stage are handed out
+// as TASKS of up to four rows to one warp each, round-robin.  A task's rows share every load of
+// the input vector (shared-memory bandwidth is what bounds an fp32 row; instruction issue an
+// int8 row), their dot-product chains interleave (ILP instead of occupancy), their totals are
+// folded with "packed" shuffle trees (kllm_device.cuh) that do the additions of cub's tree only,
+// and one lane per row runs the epilogues side by side.
+//
 // Hand-over between phases (KLLM_MEGA_TAGGED=2, default): every produced element is published as
 // one 64-bit {tag, fp32} word and polled in place by the consuming phase -- no fences, flags or
 // grid barriers; the residual-stream update after Wo and W2 is summed by the reader
-// (x = x_old + sum over ranks), which under tensor parallelism makes the same stores, sent to
-// every rank over NVLink peer mappings, the all-reduce.  One grid barrier per token remains
-// (before the argmax fold).  KLLM_MEGA_TAGGED=1 keeps grid barriers for the hand-offs inside a
-// layer, 0 uses grid barriers everywhere (single GPU only).
+// (x = x_old + sum over ranks, x_old living in the CTA's own shared memory), which under tensor
+// parallelism makes the same stores, sent to every rank over NVLink peer mappings, the
+// all-reduce.  One grid barrier per token remains (before the argmax fold).  KLLM_MEGA_TAGGED=1
+// keeps grid barriers for the hand-offs inside a layer, 0 uses grid barriers everywhere (single
+// GPU only).
 //
 // Arithmetic is the same as the per-op kernels (gemv.cu / attention.cu / elementwise.cu): every
 // dot product, reduction tree, softmax sum and value chain reproduces the reference CUDA
@@ -45,10 +53,11 @@
 namespace kllm {
 namespace mega {
 
-constexpr int kConsumerWarps = 8;
-constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kThreads = kConsumerThreads + 64;  // + the ring producer warp + the L2 prefetch warp
 constexpr int kMaxStages = 16;
+constexpr int kMaxWarps = 16;
+constexpr int kSoftmaxThreads = 256;  // mha_kernel.cu:112-127 launches 256 threads per head
+constexpr int kNormThreads = 128;     // rmsnorm_kernel.cu:58-77 launches 128 threads
+constexpr long long kSpinLimit = 120000000000LL;  // ~1 minute of SM clocks: a lost peer becomes a trap
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -105,9 +114,11 @@ __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
 }
 // 64-bit {tag, value} words of the tagged exchange: single-copy atomic, so value and tag travel
 // together and no fence or flag is needed between a writer on one GPU and a reader on another.
+__device__ __forceinline__ unsigned long long tagged_word(float v, unsigned tag) {
+  return (static_cast<unsigned long long>(tag) << 32) | __float_as_uint(v);
+}
 __device__ __forceinline__ void st_tagged(unsigned long long* p, float v, unsigned tag) {
-  const unsigned long long w = (static_cast<unsigned long long>(tag) << 32) | __float_as_uint(v);
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(tagged_word(v, tag)) : "memory");
 }
 __device__ __forceinline__ void ld_tagged2(const unsigned long long* p, unsigned long long& a,
                                            unsigned long long& b) {
@@ -115,8 +126,7 @@ __device__ __forceinline__ void ld_tagged2(const unsigned long long* p, unsigned
 }
 // local (same GPU) flavour of the tagged words
 __device__ __forceinline__ void st_tagged_gpu(unsigned long long* p, float v, unsigned tag) {
-  const unsigned long long w = (static_cast<unsigned long long>(tag) << 32) | __float_as_uint(v);
-  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(tagged_word(v, tag)) : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_tagged_gpu(const unsigned long long* p) {
   unsigned long long w;
@@ -127,23 +137,41 @@ __device__ __forceinline__ void ld_tagged2_gpu(const unsigned long long* p, unsi
                                                unsigned long long& b) {
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
-// spin until the word carries `tag` (bounded: a lost producer becomes a trap, not a hang)
+__device__ __forceinline__ unsigned tag_of(unsigned long long w) { return static_cast<unsigned>(w >> 32); }
+__device__ __forceinline__ float val_of(unsigned long long w) { return __uint_as_float(static_cast<unsigned>(w)); }
+
+// A polled word may carry an OLDER tag (its producer is still on its way) but never a NEWER one:
+// the slot-reuse argument (megakernel.h) says nobody publishes use n+1 of a word before everybody
+// consumed use n.  A newer tag is therefore a protocol error and traps at once; a word that never
+// turns up becomes a trap after a bounded spin, not a hang.
+__device__ __noinline__ void poll_failed(unsigned seen, unsigned want, long long t_start, int what) {
+  const char* names[3] = {"hand-off word", "residual exchange", "phase input"};
+  if (static_cast<int>(seen - want) > 0) {
+    printf("kllm mega: cta %d thread %d: %s carries tag %u, newer than the awaited %u (protocol error)\n",
+           blockIdx.x, threadIdx.x, names[what], seen, want);
+    __trap();
+  }
+  if (clock64() - t_start > kSpinLimit) {
+    printf("kllm mega: cta %d thread %d timed out on %s tag %u (last seen %u)\n", blockIdx.x, threadIdx.x,
+           names[what], want, seen);
+    __trap();
+  }
+}
+// spin until the word carries `tag`
 __device__ __forceinline__ float poll_tagged(const unsigned long long* p, unsigned tag) {
   unsigned long long w = ld_tagged_gpu(p);
-  if (static_cast<unsigned>(w >> 32) != tag) {
+  if (tag_of(w) != tag) {
     const long long t0 = clock64();
     do {
+      poll_failed(tag_of(w), tag, t0, 0);
       w = ld_tagged_gpu(p);
-      if (clock64() - t0 > 120000000000LL) {
-        printf("kllm mega: cta %d thread %d timed out on hand-off tag %u\n", blockIdx.x, threadIdx.x, tag);
-        __trap();
-      }
-    } while (static_cast<unsigned>(w >> 32) != tag);
+    } while (tag_of(w) != tag);
   }
-  return __uint_as_float(static_cast<unsigned>(w));
+  return val_of(w);
 }
+template <int CT>
 __device__ __forceinline__ void consumer_sync() {
-  asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+  asm volatile("bar.sync 1, %0;" ::"n"(CT) : "memory");
 }
 
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -163,16 +191,44 @@ struct Pipe {
   }
 };
 
+// Control block at the start of dynamic shared memory.  The ring leaves only a few KB of L1, so
+// everything the inner loops touch lives in shared memory or registers: the schedule entries the
+// consumers, the ring producer and the L2 prefetcher are working on (usually three different
+// phases) and a copy of the kernel parameters for the phase functions, which are real calls
+// (__noinline__): inlined into one huge kernel their row loops inherit its register pressure and
+// ptxas serialises every shared-memory load with its math.
+struct Ctl {
+  uint64_t full_bar[kMaxStages];
+  uint64_t empty_bar[kMaxStages];
+  float s_warp[kMaxWarps];
+  float s_argv[kMaxWarps];
+  int s_argi[kMaxWarps];
+  float s_bcast;
+  volatile unsigned fill_count;  // ring stages the producer has issued so far
+  Phase ph_cons, ph_prod, ph_pf;
+  Params P;
+};
+constexpr int kCtlBytes = (static_cast<int>(sizeof(Ctl)) + 127) & ~127;
+extern __shared__ __align__(128) unsigned char smem[];
+__device__ __forceinline__ Ctl& ctl() { return *reinterpret_cast<Ctl*>(smem); }
+// per-thread state the phase functions hand back to the kernel loop
+struct Carry {
+  Pipe pipe;
+  float best_v;
+  int best_i;
+};
+
 // Grid barrier over the consumer threads of all CTAs.  Monotonic counter, wrap-safe compare.
+template <int CT>
 __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target, unsigned grid) {
-  consumer_sync();
+  consumer_sync<CT>();
   target += grid;
   if (threadIdx.x == 0) {
     red_release_add(counter, 1u);
     while (static_cast<int>(ld_acquire_u32(counter) - target) < 0) {
     }
   }
-  consumer_sync();
+  consumer_sync<CT>();
 }
 
 // ---- unit -> (segment, row) ------------------------------------------------------------------
@@ -214,58 +270,166 @@ __device__ __forceinline__ int run_length(const RowRef& rr, int lane, int nrows)
 }
 
 // ---- exact-order accumulation from shared memory ----------------------------------------------
-// fp32: virtual thread (lane + 32 j) owns packs base + 32 j + lane (matmul_kernel.cu:27-35).
-// Full 128-pack blocks run branch-free with all 4*(1+NR) shared loads issued before the math
-// (two blocks in flight), so the four independent chains per row overlap the LDS latency.
+// The row loops address shared memory by 32-bit shared-window addresses through explicit
+// ld.shared: behind the call boundary of dot_rows the compiler no longer knows the pointers are
+// shared memory (it would emit generic loads), and `volatile` keeps the loads in program order --
+// a batch of loads first, then the math that consumes them.
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+
+// fp32: virtual thread (lane + 32 j) owns packs base + 32 j + lane (matmul_kernel.cu:27-35).  The
+// NR rows of a task share each load of x; per batch (two 32-pack columns) 2 x loads and 2 NR weight
+// loads are issued before the 2 NR independent dot4 chains.
 template <int NR>
-__device__ __forceinline__ void accum_f32(const float4* const (&w)[NR], const float4* x4,
-                                          int n_packs, int lane, float (&acc)[NR][4]) {
-  const int full = n_packs & ~127;
-  const float4* xp = x4 + lane;
-#pragma unroll 2
-  for (int base = 0; base < full; base += 128) {
-    float4 xv[4];
-    float4 wv[NR][4];
+struct ColF32 {  // one 32-pack column of a task: the lane's pack of x and of each of the NR rows
+  float4 x;
+  float4 w[NR];
+};
+template <int NR>
+__device__ __forceinline__ void load_col(ColF32<NR>& c, uint32_t xp, const uint32_t (&wp)[NR], uint32_t off) {
+  c.x = lds_f4(xp + off);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) xv[j] = xp[base + 32 * j];
+  for (int r = 0; r < NR; ++r) c.w[r] = lds_f4(wp[r] + off);
+}
+template <int NR, int J>
+__device__ __forceinline__ void fold_col(const ColF32<NR>& c, float (&acc)[NR][4]) {
 #pragma unroll
-    for (int r = 0; r < NR; ++r)
+  for (int r = 0; r < NR; ++r) acc[r][J] = __fadd_rn(dot4_ref(c.x, c.w[r]), acc[r][J]);
+}
+template <int NR>
+__device__ __forceinline__ void accum_f32(const uint32_t (&w)[NR], uint32_t x, int n_packs, int lane,
+                                          float (&acc)[NR][4]) {
+  const int blocks = n_packs >> 7;  // full 128-pack blocks = 4 columns of 32 packs
+  uint32_t xp = x + lane * 16;
+  uint32_t wp[NR];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) wv[r][j] = w[r][base + 32 * j + lane];
+  for (int r = 0; r < NR; ++r) wp[r] = w[r] + lane * 16;
+  // Software pipeline over the columns with two register buffers: the 1 + NR loads of the next
+  // column are in flight while the NR dot4 chains of the current one run.
+  if (blocks > 0) {
+    ColF32<NR> a, b;
+    load_col<NR>(a, xp, wp, 0);
+#pragma unroll 1
+    for (int blk = 0; blk < blocks; ++blk) {
+      load_col<NR>(b, xp, wp, 512);
+      fold_col<NR, 0>(a, acc);
+      load_col<NR>(a, xp, wp, 1024);
+      fold_col<NR, 1>(b, acc);
+      load_col<NR>(b, xp, wp, 1536);
+      fold_col<NR, 2>(a, acc);
+      xp += 2048;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int r = 0; r < NR; ++r) acc[r][j] = __fadd_rn(dot4_ref(xv[j], wv[r][j]), acc[r][j]);
+      for (int r = 0; r < NR; ++r) wp[r] += 2048;
+      if (blk + 1 < blocks) load_col<NR>(a, xp, wp, 0);
+      fold_col<NR, 3>(b, acc);
+    }
   }
+  const int full = blocks << 7;
   if (full < n_packs) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int idx = full + 32 * j + lane;
-      if (idx < n_packs) {
-        const float4 xv = x4[idx];
+      if (full + 32 * j + lane < n_packs) {
+        const float4 xv = lds_f4(xp + 512 * j);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) acc[r][j] = __fadd_rn(dot4_ref(xv, w[r][idx]), acc[r][j]);
+        for (int r = 0; r < NR; ++r) acc[r][j] = __fadd_rn(dot4_ref(xv, lds_f4(wp[r] + 512 * j)), acc[r][j]);
       }
     }
   }
 }
 
-// int8: virtual thread (4 lane + e) owns elements 128 k + 4 lane + e (matmul_kernel.cu:70-74).
-// `sc[r]` points at the row's staged scales (first group of the row at index 0; rows start on a
-// group boundary -- checked on the host).
+// int8, group size 64 (export.py --version 3): virtual thread (4 lane + e) owns elements
+// 128 k + 4 lane + e (matmul_kernel.cu:70-74), so the lane's four bytes of chunk k sit in group
+// 2 k + (lane >> 4) of the row: the scale address just steps by two floats.  Per element the
+// reference's fma(x * scale, float(w), acc) -- PRMT + FADD (exact int8 -> fp32) + FMUL + FFMA;
+// everything else (one 4-byte weight load and one scale load per row, one 16-byte x load per chunk,
+// the xor that prepares the byte permutes) is shared by four elements or by the NR rows.  Chunk
+// k + 1 is loaded while chunk k is computed.
+// `sc[r]`: the row's staged scales (rows start on a group boundary -- checked on the host).
 template <int NR>
-__device__ __forceinline__ void accum_w8(const uint32_t* const (&w)[NR], const float* const (&sc)[NR],
-                                         const float4* x4, int M, int group_shift, int group_size,
-                                         int lane, float (&acc)[NR][4]) {
+__device__ __forceinline__ void accum_w8_g64(const uint32_t (&w)[NR], const uint32_t (&sc)[NR], uint32_t x,
+                                             int M, int lane, float (&acc)[NR][4]) {
+  const int chunks = M >> 7;
+  const bool tail = (chunks << 7) + (lane << 2) < M;  // M % 128 != 0: a last, partial chunk
+  const int total = chunks + (tail ? 1 : 0);
+  if (total == 0) return;
+  uint32_t xp = x + lane * 16;
+  uint32_t wp[NR], sp[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    wp[r] = w[r] + lane * 4;
+    sp[r] = sc[r] + (lane >> 4) * 4;
+  }
+  float4 xv = lds_f4(xp);
+  uint32_t packed[NR];
+  float s[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    packed[r] = lds_u32(wp[r]);
+    s[r] = lds_f32(sp[r]);
+  }
+#pragma unroll 2
+  for (int k = 0; k < total; ++k) {
+    if (k + 1 < total) {  // uniform per virtual-thread quad: lanes past a partial tail chunk have total == chunks
+      xp += 512;
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        wp[r] += 128;
+        sp[r] += 8;
+      }
+    }
+    const float4 xn = lds_f4(xp);  // last iteration: re-reads its own chunk (harmless)
+    uint32_t pn[NR];
+    float sn[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      pn[r] = lds_u32(wp[r]);
+      sn[r] = lds_f32(sp[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      float wf[4];
+      int8x4_to_float(packed[r], wf);
+      acc[r][0] = __fmaf_rn(__fmul_rn(xv.x, s[r]), wf[0], acc[r][0]);
+      acc[r][1] = __fmaf_rn(__fmul_rn(xv.y, s[r]), wf[1], acc[r][1]);
+      acc[r][2] = __fmaf_rn(__fmul_rn(xv.z, s[r]), wf[2], acc[r][2]);
+      acc[r][3] = __fmaf_rn(__fmul_rn(xv.w, s[r]), wf[3], acc[r][3]);
+    }
+    xv = xn;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      packed[r] = pn[r];
+      s[r] = sn[r];
+    }
+  }
+}
+
+// int8, any other group size (multiple of 4): the group index is computed per chunk.
+template <int NR>
+__device__ __forceinline__ void accum_w8_any(const uint32_t (&w)[NR], const uint32_t (&sc)[NR], uint32_t x,
+                                             int M, int group_shift, int group_size, int lane,
+                                             float (&acc)[NR][4]) {
   const int full_chunks = M >> 7;
   auto one = [&](int k) {
     const int i = (k << 7) + (lane << 2);
-    const float4 xv = x4[i >> 2];
+    const float4 xv = lds_f4(x + i * 4);
     const int g = group_shift >= 0 ? (i >> group_shift) : (i / group_size);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-      const uint32_t packed = w[r][i >> 2];
-      const float s = sc[r][g];
+      const uint32_t packed = lds_u32(w[r] + i);
+      const float s = lds_f32(sc[r] + g * 4);
       float wf[4];
       int8x4_to_float(packed, wf);
       acc[r][0] = __fmaf_rn(__fmul_rn(xv.x, s), wf[0], acc[r][0]);
@@ -274,50 +438,47 @@ __device__ __forceinline__ void accum_w8(const uint32_t* const (&w)[NR], const f
       acc[r][3] = __fmaf_rn(__fmul_rn(xv.w, s), wf[3], acc[r][3]);
     }
   };
-#pragma unroll 4
+#pragma unroll 2
   for (int k = 0; k < full_chunks; ++k) one(k);
   if ((full_chunks << 7) + (lane << 2) < M) one(full_chunks);
 }
 
-// rmsnorm_kernel.cu:4-50 on x staged in shared memory (warp 0), cf. gemv.cu rms_scale_ref.
-__device__ __forceinline__ float rms_scale_smem(const float* xs, int n, float eps, int lane) {
-  const int pack_num = n >> 2;
-  const float4* xs4 = reinterpret_cast<const float4*>(xs);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const int full = pack_num & ~127;
-#pragma unroll 2
-  for (int base = 0; base < full; base += 128) {
-    float4 v[4];
+// Dot products of the NR rows of a task (shared-window addresses of the rows and of their int8
+// scales); every lane gets every total.  Deliberately NOT inlined: as part of the megakernel's one
+// big function the row loops inherit its register pressure and ptxas then serialises every
+// shared-memory load with its dependent math; as a function of their own they keep a batch of loads
+// in flight.
+struct Rows4 {
+  uint32_t a[4];
+};
+template <int NR, bool INT8>
+__device__ __forceinline__ float4 dot_rows(Rows4 rows, Rows4 scales, uint32_t x, int M, int group_size,
+                                        int group_shift, int lane) {
+  float acc[NR][4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = xs4[base + 32 * j + lane];
+  for (int r = 0; r < NR; ++r)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float s = acc[j];
-      s = __fmaf_rn(v[j].x, v[j].x, s);
-      s = __fmaf_rn(v[j].y, v[j].y, s);
-      s = __fmaf_rn(v[j].z, v[j].z, s);
-      s = __fmaf_rn(v[j].w, v[j].w, s);
-      acc[j] = s;
-    }
+    for (int j = 0; j < 4; ++j) acc[r][j] = 0.f;
+  float d[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t w[NR], sc[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    w[r] = rows.a[r];
+    sc[r] = scales.a[r];
   }
-  if (full < pack_num) {
+  if constexpr (INT8) {
+    if (group_size == 64)
+      accum_w8_g64<NR>(w, sc, x, M, lane, acc);
+    else
+      accum_w8_any<NR>(w, sc, x, M, group_shift, group_size, lane, acc);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int idx = full + 32 * j + lane;
-      if (idx < pack_num) {
-        const float4 v = xs4[idx];
-        float s = acc[j];
-        s = __fmaf_rn(v.x, v.x, s);
-        s = __fmaf_rn(v.y, v.y, s);
-        s = __fmaf_rn(v.z, v.z, s);
-        s = __fmaf_rn(v.w, v.w, s);
-        acc[j] = s;
-      }
-    }
+    for (int r = 0; r < NR; ++r) d[r] = block128_sum_quad_packed(acc[r]);
+  } else {
+    accum_f32<NR>(w, x, M >> 2, lane, acc);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) d[r] = block128_sum_vt_packed(acc[r], lane);
   }
-  float sum = block128_sum_vt(acc);
-  sum = __shfl_sync(kFull, sum, 0);
-  return rsqrtf(__fadd_rn(__fdiv_rn(sum, static_cast<float>(n)), eps));
+  return make_float4(d[0], d[1], d[2], d[3]);
 }
 
 struct ArgBest {
@@ -343,10 +504,18 @@ __device__ __forceinline__ void arg_fold(ArgBest& a, float ov, int oi) {
 // here from registers / a direct load.
 __device__ __forceinline__ int attn_tiles(int pos, int T) { return (pos + T - 1) / T; }
 
-__device__ void attention_phase(const Params& P, const Phase& ph, int head, int pos, float* ws,
-                                float* s_warp, float* s_bcast, unsigned char* stages,
-                                uint64_t* full_bar, uint64_t* empty_bar, Pipe& pipe, unsigned tag_in,
-                                unsigned tag_out) {
+template <int CW>
+__device__ __noinline__ Pipe attention_phase(int head, int pos, Pipe pipe, unsigned tag_in, unsigned tag_out) {
+  Ctl& c = ctl();
+  const Params& P = c.P;
+  const Phase& ph = c.ph_cons;
+  float* ws = reinterpret_cast<float*>(smem + kCtlBytes);
+  float* s_warp = c.s_warp;
+  float* s_bcast = &c.s_bcast;
+  unsigned char* stages = smem + kCtlBytes + P.xbuf_bytes + P.xres_bytes;
+  uint64_t* full_bar = c.full_bar;
+  uint64_t* empty_bar = c.empty_bar;
+  constexpr int CT = CW * 32;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int hs = P.head_size, seq_len = P.seq_len, T = P.attn_tile, S = P.num_stages;
@@ -395,7 +564,7 @@ __device__ void attention_phase(const Params& P, const Phase& ph, int head, int 
       kcache[(static_cast<size_t>(i1 >> 2) * seq_len + pos) * 4 + (i1 & 3)] = r1;
     }
   }
-  consumer_sync();
+  consumer_sync<CT>();
 
   // ---- scores: one left-to-right FFMA chain per timestep (mha_kernel.cu:61-91) ---------------
   const float scale = 1.f / sqrtf(static_cast<float>(hs));
@@ -436,41 +605,45 @@ __device__ void attention_phase(const Params& P, const Phase& ph, int head, int 
     }
     score_head[pos] = __fmul_rn(score, scale);
   }
-  consumer_sync();
+  consumer_sync<CT>();
 
-  // ---- softmax, mha_kernel.cu:7-45 (256 strided lanes + cub block-reduce order) -----------------
+  // ---- softmax, mha_kernel.cu:7-45: 256 strided threads + cub<256> block-reduce order (the first
+  // 256 consumer threads play them; any further warps only keep the barriers) --------------------
   const int size = pos + 1;
-  float max_val = tid < size ? score_head[tid] : -FLT_MAX;
-  for (int i = tid + kConsumerThreads; i < size; i += kConsumerThreads)
-    max_val = fmaxf(max_val, score_head[i]);
+  const bool sm_thread = tid < kSoftmaxThreads;
+  constexpr int kSmWarps = kSoftmaxThreads / 32;
+  float max_val = (sm_thread && tid < size) ? score_head[tid] : -FLT_MAX;
+  if (sm_thread)
+    for (int i = tid + kSoftmaxThreads; i < size; i += kSoftmaxThreads) max_val = fmaxf(max_val, score_head[i]);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) max_val = fmaxf(max_val, __shfl_xor_sync(kFull, max_val, off));
-  if (lane == 0) s_warp[warp] = max_val;
-  consumer_sync();
+  if (lane == 0 && sm_thread) s_warp[warp] = max_val;
+  consumer_sync<CT>();
   max_val = s_warp[0];
 #pragma unroll
-  for (int w = 1; w < kConsumerWarps; ++w) max_val = fmaxf(max_val, s_warp[w]);
-  consumer_sync();
+  for (int w = 1; w < kSmWarps; ++w) max_val = fmaxf(max_val, s_warp[w]);
+  consumer_sync<CT>();
 
   float sum = 0.0f;
-  for (int i = tid; i < size; i += kConsumerThreads) {
-    const float e = expf(score_head[i] - max_val);
-    score_head[i] = e;
-    sum += e;
-  }
+  if (sm_thread)
+    for (int i = tid; i < size; i += kSoftmaxThreads) {
+      const float e = expf(score_head[i] - max_val);
+      score_head[i] = e;
+      sum += e;
+    }
   sum = warp_tree_sum(sum);
-  if (lane == 0) s_warp[warp] = sum;
-  consumer_sync();
+  if (lane == 0 && sm_thread) s_warp[warp] = sum;
+  consumer_sync<CT>();
   if (tid == 0) {
     float total = s_warp[0];
 #pragma unroll
-    for (int w = 1; w < kConsumerWarps; ++w) total = __fadd_rn(total, s_warp[w]);
+    for (int w = 1; w < kSmWarps; ++w) total = __fadd_rn(total, s_warp[w]);
     *s_bcast = total;
   }
-  consumer_sync();
+  consumer_sync<CT>();
   sum = *s_bcast;
-  for (int i = tid; i < size; i += kConsumerThreads) score_head[i] = score_head[i] / sum;
-  consumer_sync();
+  for (int i = tid; i < size; i += CT) score_head[i] = score_head[i] / sum;
+  consumer_sync<CT>();
 
   // ---- weighted value sum, mha_kernel.cu:97-109: one FFMA chain per output element ----------------
   float value = 0.0f;
@@ -495,47 +668,471 @@ __device__ void attention_phase(const Params& P, const Phase& ph, int head, int 
     else
       P.attn_out[static_cast<size_t>(head) * hs + tid] = value;
   }
+  return pipe;
 }
 
-// ---- the kernel ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t full_bar[kMaxStages];
-  __shared__ uint64_t empty_bar[kMaxStages];
-  __shared__ float s_warp[kConsumerWarps];
-  __shared__ float s_bcast;
-  __shared__ float s_argv[kConsumerWarps];
-  __shared__ int s_argi[kConsumerWarps];
-  // The ring leaves only a few KB of L1, so everything the inner loops touch lives in shared
-  // memory or registers: the consumer's and the producer's current schedule entries are copied
-  // here (they are usually in different phases).
-  __shared__ Phase s_phase_cons;
-  __shared__ Phase s_phase_prod;
-  __shared__ Phase s_phase_pf;
-  __shared__ volatile unsigned s_fill_count;  // ring stages the producer has issued so far
+// ---- staging of a tagged input vector ------------------------------------------------------------
+// Residual exchange (tp_in): x = x_old + (p_0 + ... + p_{W-1}); the partials of every rank (this
+// one included) arrive as tagged words in this rank's exchange area and are polled in place; x_old
+// is the CTA's own copy of the residual stream in shared memory (xres), updated here.  Thread t
+// handles packs t, t + NT, ...; UP packs x W ranks x 2 loads are in flight per poll round.
+// With W == 1 and FOLD the rmsnorm sum of squares is accumulated in the same pass by the
+// kNormThreads threads that own the reference's chains (rmsnorm_kernel.cu:19-32).
+template <int W, int UP, bool FOLD>
+__device__ __forceinline__ float stage_exchange(const Params& P, unsigned tag, int n4, int t, int NT,
+                                                float4* xs4, float4* xres4) {
+  const unsigned long long* area = P.tp_data[P.tp_rank] + static_cast<size_t>(tag & 1u) * W * P.tp_stride;
+  float ssq = 0.f;
+  const long long t_start = clock64();
+  for (int pb = t; pb < n4; pb += NT * UP) {
+    unsigned long long wd[UP][W][4];
+    bool ok;
+    unsigned seen = tag;
+    do {
+      ok = true;
+#pragma unroll
+      for (int k = 0; k < UP; ++k) {
+        const int p = pb + k * NT;
+        if (p < n4) {
+#pragma unroll
+          for (int r = 0; r < W; ++r) {
+            const unsigned long long* row = area + static_cast<size_t>(r) * P.tp_stride + 4 * p;
+            if (W == 1) {
+              ld_tagged2_gpu(row, wd[k][r][0], wd[k][r][1]);
+              ld_tagged2_gpu(row + 2, wd[k][r][2], wd[k][r][3]);
+            } else {
+              ld_tagged2(row, wd[k][r][0], wd[k][r][1]);
+              ld_tagged2(row + 2, wd[k][r][2], wd[k][r][3]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < UP; ++k) {
+        if (pb + k * NT < n4) {
+#pragma unroll
+          for (int r = 0; r < W; ++r)
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (tag_of(wd[k][r][e]) != tag) {
+                ok = false;
+                seen = tag_of(wd[k][r][e]);
+              }
+        }
+      }
+      if (!ok) poll_failed(seen, tag, t_start, 1);
+    } while (!ok);
+#pragma unroll
+    for (int k = 0; k < UP; ++k) {
+      const int p = pb + k * NT;
+      if (p < n4) {
+        float s[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          s[e] = val_of(wd[k][0][e]);
+#pragma unroll
+          for (int r = 1; r < W; ++r) s[e] = __fadd_rn(s[e], val_of(wd[k][r][e]));  // rank order
+        }
+        float4 x = xres4[p];
+        x.x = __fadd_rn(x.x, s[0]);  // llama3.cpp:683,719: x + out
+        x.y = __fadd_rn(x.y, s[1]);
+        x.z = __fadd_rn(x.z, s[2]);
+        x.w = __fadd_rn(x.w, s[3]);
+        xres4[p] = x;
+        xs4[p] = x;
+        if (FOLD) {
+          ssq = __fmaf_rn(x.x, x.x, ssq);
+          ssq = __fmaf_rn(x.y, x.y, ssq);
+          ssq = __fmaf_rn(x.z, x.z, ssq);
+          ssq = __fmaf_rn(x.w, x.w, ssq);
+        }
+      }
+    }
+  }
+  return ssq;
+}
 
-  float* xs = reinterpret_cast<float*>(smem);
-  unsigned char* stages = smem + P.xbuf_bytes;
+// Local hand-off (tag_in): the previous phase's output vector, polled in place.
+template <int UP>
+__device__ __forceinline__ void stage_handoff(const unsigned long long* src, unsigned tag, int n4, int t, int NT,
+                                              float4* xs4) {
+  const long long t_start = clock64();
+  for (int pb = t; pb < n4; pb += NT * UP) {
+    unsigned long long wd[UP][4];
+    bool ok;
+    unsigned seen = tag;
+    do {
+      ok = true;
+#pragma unroll
+      for (int k = 0; k < UP; ++k) {
+        const int p = pb + k * NT;
+        if (p < n4) {
+          ld_tagged2_gpu(src + 4 * p, wd[k][0], wd[k][1]);
+          ld_tagged2_gpu(src + 4 * p + 2, wd[k][2], wd[k][3]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < UP; ++k)
+        if (pb + k * NT < n4)
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (tag_of(wd[k][e]) != tag) {
+              ok = false;
+              seen = tag_of(wd[k][e]);
+            }
+      if (!ok) poll_failed(seen, tag, t_start, 2);
+    } while (!ok);
+#pragma unroll
+    for (int k = 0; k < UP; ++k) {
+      const int p = pb + k * NT;
+      if (p < n4) xs4[p] = make_float4(val_of(wd[k][0]), val_of(wd[k][1]), val_of(wd[k][2]), val_of(wd[k][3]));
+    }
+  }
+}
+
+// ---- one GEMV phase of one CTA's consumer warps --------------------------------------------------
+// Stages the phase's input vector (tagged residual exchange / tagged hand-off / plain vector) into
+// shared memory, RMS-normalises it when the phase asks for it, consumes this CTA's ring stages
+// task by task, runs the epilogues and, for the classifier, leaves the CTA's (max, index).
+template <int CW, bool INT8, bool PROF>
+__device__ __noinline__ Carry gemv_phase(Carry carry, int tok, int pos, const float* emb_row,
+                                         unsigned long long* stamp) {
+  constexpr int CT = CW * 32;
+  constexpr int wbytes = INT8 ? 1 : 4;
+  Ctl& c = ctl();
+  const Params& P = c.P;
+  const Phase& ph = c.ph_cons;
+  uint64_t* full_bar = c.full_bar;
+  uint64_t* empty_bar = c.empty_bar;
+  float* s_warp = c.s_warp;
+  float* s_argv = c.s_argv;
+  int* s_argi = c.s_argi;
+  float* xs = reinterpret_cast<float*>(smem + kCtlBytes);                  // phase input vector
+  float* xres = reinterpret_cast<float*>(smem + kCtlBytes + P.xbuf_bytes);  // residual stream (tagged modes)
+  unsigned char* stages = smem + kCtlBytes + P.xbuf_bytes + P.xres_bytes;
+  float4* xs4w = reinterpret_cast<float4*>(xs);
+  float4* xres4 = reinterpret_cast<float4*>(xres);
+  const float4* xs4 = reinterpret_cast<const float4*>(xs);
   const int S = P.num_stages;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const bool is_producer = warp == kConsumerWarps;
+  const int cta = blockIdx.x;
+  const int G = gridDim.x;
+  Pipe pipe = carry.pipe;
+  ArgBest best{carry.best_v, carry.best_i};
+  if (!PROF) stamp = nullptr;
+  auto hand_tag = [&](int hand) {
+    return P.hand_base + static_cast<unsigned>(tok * P.hands_per_token + hand) + 1u;
+  };
+
+  // ---- stage the input vector (and RMS-normalise it) --------------------------------------
+  const int M = ph.in_dim;
+  const int n4 = M >> 2;
+  const bool has_norm = ph.norm_w != nullptr;
+  // up to kMaxNormRegs float4 of the (static) norm weight ride in registers while x arrives
+  constexpr int kMaxNormRegs = (4 * 256) / CT;
+  float4 nw[kMaxNormRegs];
+  const bool norm_regs = has_norm && n4 <= kMaxNormRegs * CT;
+  if (norm_regs) {
+    const float4* nw4 = reinterpret_cast<const float4*>(ph.norm_w);
+#pragma unroll
+    for (int k = 0; k < kMaxNormRegs; ++k) {
+      const int i = tid + k * CT;
+      if (i < n4) nw[k] = __ldg(nw4 + i);
+    }
+  }
+  float ssq = 0.f;
+  bool ssq_ready = false;
+  if (ph.tp_in) {
+    // x = x_old + (p_0 + ... + p_{W-1}); no grid barrier, no all-reduce kernel
+    const unsigned tag = P.tp_seq_base + static_cast<unsigned>(tok * P.exch_per_token + ph.exch) + 1u;
+    switch (P.tp_world) {
+      case 1:
+        if (has_norm) {
+          if (tid < kNormThreads) ssq = stage_exchange<1, 4, true>(P, tag, n4, tid, kNormThreads, xs4w, xres4);
+          ssq_ready = true;
+        } else {
+          stage_exchange<1, 4, false>(P, tag, n4, tid, CT, xs4w, xres4);
+        }
+        break;
+      case 2: stage_exchange<2, 2, false>(P, tag, n4, tid, CT, xs4w, xres4); break;
+      case 4: stage_exchange<4, 1, false>(P, tag, n4, tid, CT, xs4w, xres4); break;
+      default: stage_exchange<8, 1, false>(P, tag, n4, tid, CT, xs4w, xres4); break;
+    }
+  } else if (ph.tag_in != nullptr) {
+    stage_handoff<4>(ph.tag_in, hand_tag(ph.hand_in), n4, tid, CT, xs4w);
+  } else {
+    const float4* xg4 = reinterpret_cast<const float4*>(ph.x_from_emb ? emb_row : ph.x);
+    for (int i = tid; i < n4; i += CT) xs4w[i] = __ldcg(xg4 + i);
+  }
+  if (stamp) stamp[10] = global_ns();
+  if (has_norm) {
+    // rmsnorm_kernel.cu:4-50: 128 threads, thread t sums the squares of packs t, t+128, ... with
+    // one FFMA chain, cub<128> block reduction, rsqrt(mean + eps), then (scale * x) * w
+    if (!ssq_ready) {
+      consumer_sync<CT>();
+      if (tid < kNormThreads)
+        for (int p = tid; p < n4; p += kNormThreads) {
+          const float4 v = xs4[p];
+          ssq = __fmaf_rn(v.x, v.x, ssq);
+          ssq = __fmaf_rn(v.y, v.y, ssq);
+          ssq = __fmaf_rn(v.z, v.z, ssq);
+          ssq = __fmaf_rn(v.w, v.w, ssq);
+        }
+    }
+    if (tid < kNormThreads) {
+      const float ws = warp_tree_sum(ssq);
+      if (lane == 0) s_warp[warp] = ws;
+    }
+    consumer_sync<CT>();
+    const float total = __fadd_rn(__fadd_rn(__fadd_rn(s_warp[0], s_warp[1]), s_warp[2]), s_warp[3]);
+    const float sc = rsqrtf(__fadd_rn(__fdiv_rn(total, static_cast<float>(M)), ph.norm_eps));
+    if (norm_regs) {
+#pragma unroll
+      for (int k = 0; k < kMaxNormRegs; ++k) {
+        const int i = tid + k * CT;
+        if (i < n4) {
+          float4 v = xs4w[i];
+          v.x = __fmul_rn(__fmul_rn(sc, v.x), nw[k].x);
+          v.y = __fmul_rn(__fmul_rn(sc, v.y), nw[k].y);
+          v.z = __fmul_rn(__fmul_rn(sc, v.z), nw[k].z);
+          v.w = __fmul_rn(__fmul_rn(sc, v.w), nw[k].w);
+          xs4w[i] = v;
+        }
+      }
+    } else {
+      for (int i = tid; i < M; i += CT) xs[i] = __fmul_rn(__fmul_rn(sc, xs[i]), ph.norm_w[i]);
+    }
+  }
+  consumer_sync<CT>();
+  if (stamp) stamp[1] = global_ns();
+
+  const int u0 = static_cast<int>(static_cast<long long>(cta) * ph.units / G);
+  const int u1 = static_cast<int>(static_cast<long long>(cta + 1) * ph.units / G);
+  const int rpu = ph.swiglu ? 2 : 1;
+  const int row_bytes = M * wbytes;
+  const float* residual = ph.residual_from_emb ? emb_row : ph.residual;
+
+  // bias / residual of a row are fetched BEFORE its dot product so their L2 latency hides
+  // behind the accumulation (by the lane that will run the row's epilogue)
+  auto prefetch_addend = [&](int unit, float& bias_v, float& res_v) {
+    bias_v = 0.f, res_v = 0.f;
+    if (ph.swiglu) return;
+    const RowRef rr = resolve_row(ph, unit, 0);
+    if (ph.seg[rr.seg].bias != nullptr) bias_v = __ldg(ph.seg[rr.seg].bias + rr.row);
+    if (residual != nullptr) res_v = __ldcg(residual + rr.row);
+  };
+  // one lane per unit
+  auto epilogue = [&](int unit, float d0, float d1, float bias_v, float res_v) {
+    if (ph.swiglu) {
+      const float g = swiglu_ref(d0, d1);
+      if (ph.seg[0].tag_out != nullptr)
+        st_tagged_gpu(ph.seg[0].tag_out + unit, g, hand_tag(ph.hand_out));
+      else
+        ph.seg[0].out[unit] = g;
+      return;
+    }
+    if (ph.tp_out) {
+      const unsigned tag = P.tp_seq_base + static_cast<unsigned>(tok * P.exch_per_token + ph.exch) + 1u;
+      const size_t off = (static_cast<size_t>(tag & 1u) * P.tp_world + P.tp_rank) * P.tp_stride + unit;
+      if (P.tp_world == 1) {
+        st_tagged_gpu(P.tp_data[0] + off, d0, tag);
+      } else {
+        for (int k = 1; k <= P.tp_world; ++k) st_tagged(P.tp_data[(P.tp_rank + k) % P.tp_world] + off, d0, tag);
+      }
+      return;
+    }
+    const RowRef rr = resolve_row(ph, unit, 0);
+    const Seg& sg = ph.seg[rr.seg];
+    float v = d0;
+    if (sg.bias != nullptr) v = __fadd_rn(v, bias_v);       // matmul.cpp:74-77: out + bias
+    if (residual != nullptr) v = __fadd_rn(res_v, v);       // llama3.cpp:683,719: x + out
+    if (sg.tag_out != nullptr) st_tagged_gpu(sg.tag_out + rr.row, v, hand_tag(ph.hand_out));
+    if (sg.out == nullptr) {
+    } else if (sg.head_major) {
+      const int hs = P.head_size;
+      sg.out[(static_cast<size_t>(rr.row / hs) * P.seq_len + pos) * hs + rr.row % hs] = v;
+    } else {
+      sg.out[static_cast<long long>(pos) * sg.pos_stride + rr.row] = v;
+    }
+    if (ph.argmax) arg_fold(best, v, rr.row);
+  };
+
+  long long cyc_wait = 0, cyc_rows = 0;
+  long long cyc4[4] = {0, 0, 0, 0};
+  if (ph.chunks_per_row == 1) {
+    // A stage holds n units; they are handed out as tasks of up to 4 rows (plain: 4 units, SwiGLU:
+    // 2 units = w1 + w3 rows of two outputs), task after task round-robin over the consumer warps.
+    const int ups = ph.rows_per_stage / rpu;
+    const int upt = ph.swiglu ? 2 : 4;  // units per task
+    int task = 0;                      // tasks of this phase so far (same count in every warp)
+    for (int u = u0; u < u1; u += ups) {
+      const int n = min(ups, u1 - u);
+      const long long c0 = stamp ? clock64() : 0;
+      mbar_wait(&full_bar[pipe.slot], pipe.parity);
+      const long long c1 = stamp ? clock64() : 0;
+      cyc_wait += c1 - c0;
+      const unsigned char* sbase = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
+      for (int i0 = 0; i0 < n; i0 += upt, ++task) {
+        if ((task & (CW - 1)) != warp) continue;
+        const int nu = min(upt, n - i0);
+        const long long t_a = stamp ? clock64() : 0;
+        float bias_v = 0.f, res_v = 0.f;
+        if (lane < nu) prefetch_addend(u + i0 + lane, bias_v, res_v);
+        const long long t_b = stamp ? clock64() : 0;
+        float e0 = 0.f, e1 = 0.f;  // this lane's unit: its dot product(s)
+        // shared-window addresses of the stage's rows / scale rows
+        const uint32_t rb = static_cast<uint32_t>(row_bytes), srb = static_cast<uint32_t>(ph.scale_row_bytes);
+        const uint32_t wa = smem_u32(sbase), sa = smem_u32(sbase) + static_cast<uint32_t>(ph.scale_off);
+        const uint32_t xa = smem_u32(xs);
+        if (ph.swiglu) {
+          // stage order: w1 rows of the n units, then their w3 rows
+          if (nu == 2) {
+            const Rows4 rp{{wa + i0 * rb, wa + (n + i0) * rb, wa + (i0 + 1) * rb, wa + (n + i0 + 1) * rb}};
+            const Rows4 sp{{sa + i0 * srb, sa + (n + i0) * srb, sa + (i0 + 1) * srb, sa + (n + i0 + 1) * srb}};
+            const float4 d = dot_rows<4, INT8>(rp, sp, xa, M, ph.group_size, ph.group_shift, lane);
+            e0 = lane == 0 ? d.x : d.z;
+            e1 = lane == 0 ? d.y : d.w;
+          } else {
+            const Rows4 rp{{wa + i0 * rb, wa + (n + i0) * rb, 0u, 0u}};
+            const Rows4 sp{{sa + i0 * srb, sa + (n + i0) * srb, 0u, 0u}};
+            const float4 d = dot_rows<2, INT8>(rp, sp, xa, M, ph.group_size, ph.group_shift, lane);
+            e0 = d.x, e1 = d.y;
+          }
+        } else if (nu == 4) {
+          const Rows4 rp{{wa + i0 * rb, wa + (i0 + 1) * rb, wa + (i0 + 2) * rb, wa + (i0 + 3) * rb}};
+          const Rows4 sp{{sa + i0 * srb, sa + (i0 + 1) * srb, sa + (i0 + 2) * srb, sa + (i0 + 3) * srb}};
+          const float4 d = dot_rows<4, INT8>(rp, sp, xa, M, ph.group_size, ph.group_shift, lane);
+          e0 = lane == 0 ? d.x : lane == 1 ? d.y : lane == 2 ? d.z : d.w;
+        } else {
+          int r0 = 0;
+          if (nu >= 2) {
+            const Rows4 rp{{wa + i0 * rb, wa + (i0 + 1) * rb, 0u, 0u}};
+            const Rows4 sp{{sa + i0 * srb, sa + (i0 + 1) * srb, 0u, 0u}};
+            const float4 d = dot_rows<2, INT8>(rp, sp, xa, M, ph.group_size, ph.group_shift, lane);
+            e0 = lane == 0 ? d.x : d.y;
+            r0 = 2;
+          }
+          if (r0 < nu) {  // nu is 1 or 3: one more row
+            const Rows4 rp{{wa + (i0 + r0) * rb, 0u, 0u, 0u}};
+            const Rows4 sp{{sa + (i0 + r0) * srb, 0u, 0u, 0u}};
+            const float4 d = dot_rows<1, INT8>(rp, sp, xa, M, ph.group_size, ph.group_shift, lane);
+            if (lane == r0) e0 = d.x;
+          }
+        }
+        const long long t_c = stamp ? clock64() : 0;
+        if (lane < nu) epilogue(u + i0 + lane, e0, e1, bias_v, res_v);
+        if (stamp) {
+          cyc4[0] += t_b - t_a, cyc4[1] += t_c - t_b, cyc4[3] += clock64() - t_c;
+        }
+      }
+      __syncwarp();
+      if (stamp) cyc_rows += clock64() - c1;
+      if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
+      pipe.advance(S);
+    }
+  } else {
+    // rows longer than a stage (fp32 only): the owning warp carries its partial sums across
+    // consecutive stages; chunk boundaries are multiples of 128 packs so every virtual
+    // thread still sees its packs in increasing order.
+    for (int u = u0; u < u1; ++u) {
+      const bool mine = ((u - u0) & (CW - 1)) == warp;
+      float bias_v = 0.f, res_v = 0.f;
+      if (mine && lane == 0) prefetch_addend(u, bias_v, res_v);
+      float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+      for (int c = 0; c < ph.chunks_per_row; ++c) {
+        const int e0 = c * ph.chunk_elems;
+        const int ne = min(ph.chunk_elems, M - e0);
+        mbar_wait(&full_bar[pipe.slot], pipe.parity);
+        if (mine) {
+          const uint32_t w[1] = {smem_u32(stages + static_cast<size_t>(pipe.slot) * P.stage_bytes)};
+          accum_f32<1>(w, smem_u32(xs) + static_cast<uint32_t>(e0) * 4u, ne >> 2, lane, acc);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
+        pipe.advance(S);
+      }
+      if (mine) {
+        const float d0 = block128_sum_vt_packed(acc[0], lane);
+        if (lane == 0) epilogue(u, d0, 0.f, bias_v, res_v);
+      }
+    }
+  }
+
+  if (ph.argmax) {
+    // per-CTA (max, lowest index) of the classifier rows this CTA produced: the (up to four) lanes
+    // that ran epilogues hold partial bests
+    ArgBest wb = best;
+#pragma unroll
+    for (int off = 1; off < 4; off <<= 1) {
+      const float ov = __shfl_xor_sync(kFull, wb.v, off);
+      const int oi = __shfl_xor_sync(kFull, wb.i, off);
+      arg_fold(wb, ov, oi);
+    }
+    if (lane == 0) {
+      s_argv[warp] = wb.v;
+      s_argi[warp] = wb.i;
+    }
+    consumer_sync<CT>();
+    if (tid == 0) {
+      ArgBest b{0.f, -1};
+      for (int w = 0; w < CW; ++w) arg_fold(b, s_argv[w], s_argi[w]);
+      P.arg_val[cta] = b.v;
+      P.arg_idx[cta] = b.i;
+    }
+  }
+  if (stamp) {
+    stamp[2] = global_ns();
+    stamp[4] = static_cast<unsigned long long>(cyc4[0]);
+    stamp[5] = static_cast<unsigned long long>(cyc4[1]);
+    stamp[6] = static_cast<unsigned long long>(cyc4[2]);
+    stamp[7] = static_cast<unsigned long long>(cyc4[3]);
+    stamp[8] = static_cast<unsigned long long>(cyc_wait);
+    stamp[9] = static_cast<unsigned long long>(cyc_rows);
+  }
+  return Carry{pipe, best.v, best.i};
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------
+template <int CW, bool INT8, bool PROF>
+__global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Params P) {
+  constexpr int CT = CW * 32;  // consumer threads
+  Ctl& c = ctl();
+  uint64_t* full_bar = c.full_bar;
+  uint64_t* empty_bar = c.empty_bar;
+  Phase& s_phase_cons = c.ph_cons;
+  Phase& s_phase_prod = c.ph_prod;
+  Phase& s_phase_pf = c.ph_pf;
+  volatile unsigned& s_fill_count = c.fill_count;
+
+  float* xres = reinterpret_cast<float*>(smem + kCtlBytes + P.xbuf_bytes);  // residual stream (tagged modes)
+  unsigned char* stages = smem + kCtlBytes + P.xbuf_bytes + P.xres_bytes;
+  const int S = P.num_stages;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const bool is_producer = warp == CW;
   const int cta = blockIdx.x;
   const int G = gridDim.x;
 
+  {  // the phase functions read the kernel parameters from shared memory
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&P);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&c.P);
+    for (int i = tid; i < static_cast<int>(sizeof(Params) / 4); i += CT + 64) dst[i] = src[i];
+  }
   if (tid == 0) {
     s_fill_count = 0u;
     for (int s = 0; s < S; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kConsumerWarps);
+      mbar_init(&empty_bar[s], CW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
   Pipe pipe{0, 0u};
-  const int wbytes = P.group_size > 0 ? 1 : 4;
+  constexpr int wbytes = INT8 ? 1 : 4;
 
   // =============================== producer warp ===============================================
   if (is_producer) {
@@ -553,10 +1150,6 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
           __syncwarp();
         }
         const Phase& ph = s_phase_prod;
-        unsigned long long* pstamp = (P.prof != nullptr && tok == P.prof_token && lane == 0)
-                                         ? P.prof + (static_cast<size_t>(cta) * P.n_phases + pi) * kProfStamps
-                                         : nullptr;
-        (void)pstamp;
         if (ph.kind == kPhaseAttention) {
           if (cta >= P.head_num || ppos == 0) continue;
           // rows t < pos of this head: final since the previous token.  Order the async-proxy
@@ -586,7 +1179,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
               if (lane == 0) mbar_expect_tx(&full_bar[pipe.slot], static_cast<uint32_t>(nt) * hs * 4);
               __syncwarp();
               if (kv == 0) {
-                if (lane < (hs >> 2))
+                if (lane < (hs >> 2))  // hs <= 128 (checked on the host): one 16-byte chunk column per lane
                   bulk_g2s(dst + static_cast<size_t>(lane) * T * 16,
                            kbase + (static_cast<size_t>(lane) * P.seq_len + t0) * 4,
                            static_cast<uint32_t>(nt) * 16, &full_bar[pipe.slot], policy_kv);
@@ -655,7 +1248,6 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
             }
           }
         }
-        
       }
     }
     return;
@@ -667,7 +1259,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
   // walks the same weight schedule as the producer, pf_stages ring-stages AHEAD of it, and only
   // pulls the bytes into L2 (cp.async.bulk.prefetch.L2): the outstanding window keeps HBM
   // streaming while the SMs wait for each other, and the ring then refills from L2.
-  if (warp == kConsumerWarps + 1) {
+  if (warp == CW + 1) {
     if (P.pf_stages <= 0) return;
     unsigned ahead = 0u;  // stages walked by this warp (same counting as the producer's `filled`)
     int ppos = P.state->pos;
@@ -738,12 +1330,19 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
   if (static_cast<unsigned>(token) >= static_cast<unsigned>(P.vocab_size)) token = 0;
   int pos = P.state->pos;
   int step = P.state->step;
+  float4* xres4 = reinterpret_cast<float4*>(xres);
 
   for (int tok = 0; tok < P.n_tokens; ++tok) {
     const float* emb_row = P.tok_emb + static_cast<size_t>(token) * P.dim;
     ArgBest best{0.f, -1};
+    if (P.xres_bytes) {
+      // the residual stream starts as the embedding row (llama3.cpp:578-598); the previous token's
+      // last reader of xres (classifier staging) is behind the grid barrier that closed that token
+      const float4* e4 = reinterpret_cast<const float4*>(emb_row);
+      for (int i = tid; i < (P.dim >> 2); i += CT) xres4[i] = __ldg(e4 + i);
+    }
 
-    const bool prof_on = P.prof != nullptr && tok == P.prof_token && tid == 0;
+    const bool prof_on = PROF && P.prof != nullptr && tok == P.prof_token && tid == 0;
     bool prev_barrier = true;
     auto hand_tag = [&](int hand) {
       return P.hand_base + static_cast<unsigned>(tok * P.hands_per_token + hand) + 1u;
@@ -752,385 +1351,34 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
       {
         // the grid barrier that ended the previous phase is the hazard fence for this copy; a
         // phase closed by a tagged exchange has none, so fence the CTA's own warps here
-        if (!prev_barrier) consumer_sync();
+        if (!prev_barrier) consumer_sync<CT>();
         const uint32_t* src = reinterpret_cast<const uint32_t*>(P.phases + pi);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&s_phase_cons);
-        static_assert(sizeof(Phase) / 4 <= kConsumerThreads, "phase copy");
+        static_assert(sizeof(Phase) / 4 <= CT, "phase copy");
         if (tid < static_cast<int>(sizeof(Phase) / 4)) dst[tid] = __ldg(src + tid);
-        consumer_sync();
+        consumer_sync<CT>();
       }
       const Phase& ph = s_phase_cons;
       unsigned long long* stamp =
-          prof_on ? P.prof + (static_cast<size_t>(cta) * P.n_phases + pi) * kProfStamps : nullptr;
+          (PROF && prof_on) ? P.prof + (static_cast<size_t>(cta) * P.n_phases + pi) * kProfStamps : nullptr;
       if (stamp) stamp[0] = global_ns();
 
       if (ph.kind == kPhaseAttention) {
-        if (cta < P.head_num)
-          attention_phase(P, ph, cta, pos, xs, s_warp, &s_bcast, stages, full_bar, empty_bar, pipe,
-                          hand_tag(ph.hand_in), hand_tag(ph.hand_out));
+        if (cta < P.head_num) pipe = attention_phase<CW>(cta, pos, pipe, hand_tag(ph.hand_in), hand_tag(ph.hand_out));
         if (stamp) stamp[1] = stamp[2] = global_ns();
-        if (ph.barrier_after) grid_barrier(P.barrier, bar_target, G);
+        if (ph.barrier_after) grid_barrier<CT>(P.barrier, bar_target, G);
         prev_barrier = ph.barrier_after != 0;
         if (stamp) stamp[3] = global_ns();
         continue;
       }
       prev_barrier = ph.barrier_after != 0;
 
-      // ---- stage the input vector (and RMS-normalise it) --------------------------------------
-      const int M = ph.in_dim;
-      if (ph.tp_in) {
-        // x = x_old + (p_0 + ... + p_{W-1}); the partials arrive as tagged words from every rank
-        // (this one included) and are polled in place: no grid barrier, no all-reduce kernel.
-        const unsigned tag = P.tp_seq_base + static_cast<unsigned>(tok * P.exch_per_token + ph.exch) + 1u;
-        const int W = P.tp_world;
-        const unsigned long long* area =
-            P.tp_data[P.tp_rank] + static_cast<size_t>(tag & 1u) * W * P.tp_stride;
-        const float* xo = ph.x_old != nullptr ? ph.x_old : emb_row;
-        const int s0 = static_cast<int>(static_cast<long long>(cta) * M / G);
-        const int s1 = static_cast<int>(static_cast<long long>(cta + 1) * M / G);
-        const int pairs = M >> 1;
-        const long long t_start = clock64();
-        for (int base = 0; base < pairs; base += 4 * kConsumerThreads) {
-          float acc[4][2];
-          float xold[4][2];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int pr = base + k * kConsumerThreads + tid;
-            if (pr < pairs) {
-              const float2 v = __ldcg(reinterpret_cast<const float2*>(xo) + pr);
-              xold[k][0] = v.x, xold[k][1] = v.y;
-            }
-          }
-          // two ranks per round trip (their loads are all in flight together), summed in rank order
-          for (int r0 = 0; r0 < W; r0 += 2) {
-            const bool two = r0 + 1 < W;
-            const unsigned long long* row0 = area + static_cast<size_t>(r0) * P.tp_stride;
-            const unsigned long long* row1 = row0 + (two ? P.tp_stride : 0);
-            unsigned long long w[2][4][2];
-            bool ok;
-            do {
-              ok = true;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int pr = base + k * kConsumerThreads + tid;
-                if (pr < pairs) {
-                  ld_tagged2(row0 + 2 * pr, w[0][k][0], w[0][k][1]);
-                  if (two) ld_tagged2(row1 + 2 * pr, w[1][k][0], w[1][k][1]);
-                }
-              }
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int pr = base + k * kConsumerThreads + tid;
-                if (pr < pairs) {
-                  ok = ok && static_cast<unsigned>(w[0][k][0] >> 32) == tag &&
-                       static_cast<unsigned>(w[0][k][1] >> 32) == tag;
-                  if (two)
-                    ok = ok && static_cast<unsigned>(w[1][k][0] >> 32) == tag &&
-                         static_cast<unsigned>(w[1][k][1] >> 32) == tag;
-                }
-              }
-              if (!ok && clock64() - t_start > 120000000000LL) {
-                printf("kllm mega: rank %d cta %d timed out on exchange tag %u from ranks %d..%d\n", P.tp_rank, cta,
-                       tag, r0, r0 + (two ? 1 : 0));
-                __trap();
-              }
-            } while (!ok);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (base + k * kConsumerThreads + tid >= pairs) continue;
-#pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                if (j == 1 && !two) continue;
-                const float a = __uint_as_float(static_cast<unsigned>(w[j][k][0]));
-                const float b = __uint_as_float(static_cast<unsigned>(w[j][k][1]));
-                acc[k][0] = (r0 + j) == 0 ? a : __fadd_rn(acc[k][0], a);
-                acc[k][1] = (r0 + j) == 0 ? b : __fadd_rn(acc[k][1], b);
-              }
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int pr = base + k * kConsumerThreads + tid;
-            if (pr < pairs) {
-              const float x0 = __fadd_rn(xold[k][0], acc[k][0]);  // llama3.cpp:683,719: x + out
-              const float x1 = __fadd_rn(xold[k][1], acc[k][1]);
-              xs[2 * pr] = x0, xs[2 * pr + 1] = x1;
-              if (2 * pr >= s0 && 2 * pr < s1) ph.x_new[2 * pr] = x0;
-              if (2 * pr + 1 >= s0 && 2 * pr + 1 < s1) ph.x_new[2 * pr + 1] = x1;
-            }
-          }
-        }
-        consumer_sync();
-      }
-      if (ph.tag_in != nullptr) {
-        // the previous phase's output vector, polled in place (no barrier in between)
-        const unsigned tag = hand_tag(ph.hand_in);
-        const int pairs = M >> 1;
-        const long long t_start = clock64();
-        for (int base = 0; base < pairs; base += 4 * kConsumerThreads) {
-          unsigned long long w[4][2];
-          bool ok;
-          do {
-            ok = true;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int pr = base + k * kConsumerThreads + tid;
-              if (pr < pairs) ld_tagged2_gpu(ph.tag_in + 2 * pr, w[k][0], w[k][1]);
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int pr = base + k * kConsumerThreads + tid;
-              if (pr < pairs)
-                ok = ok && static_cast<unsigned>(w[k][0] >> 32) == tag && static_cast<unsigned>(w[k][1] >> 32) == tag;
-            }
-            if (!ok && clock64() - t_start > 120000000000LL) {
-              printf("kllm mega: cta %d timed out on hand-off tag %u (phase input)\n", cta, tag);
-              __trap();
-            }
-          } while (!ok);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int pr = base + k * kConsumerThreads + tid;
-            if (pr < pairs) {
-              xs[2 * pr] = __uint_as_float(static_cast<unsigned>(w[k][0]));
-              xs[2 * pr + 1] = __uint_as_float(static_cast<unsigned>(w[k][1]));
-            }
-          }
-        }
-        consumer_sync();
-      }
       {
-        const float* xg = ph.x_from_emb ? emb_row : ph.x;
-        const float4* xg4 = reinterpret_cast<const float4*>(xg);
-        float4* xs4w = reinterpret_cast<float4*>(xs);
-        const int n4 = M >> 2;
-        // up to kMaxNormRegs float4 of the (static) norm weight ride in registers while x arrives
-        constexpr int kMaxNormRegs = 4;
-        float4 nw[kMaxNormRegs];
-        const float4* nw4 = reinterpret_cast<const float4*>(ph.norm_w);
-        const bool norm_regs = ph.norm_w != nullptr && n4 <= kMaxNormRegs * kConsumerThreads;
-        if (norm_regs) {
-#pragma unroll
-          for (int k = 0; k < kMaxNormRegs; ++k) {
-            const int i = tid + k * kConsumerThreads;
-            if (i < n4) nw[k] = __ldg(nw4 + i);
-          }
-        }
-        if (!ph.tp_in && ph.tag_in == nullptr) {
-          for (int i = tid; i < n4; i += kConsumerThreads) xs4w[i] = __ldcg(xg4 + i);
-          consumer_sync();
-        }
-        if (stamp) stamp[10] = global_ns();
-        if (ph.norm_w != nullptr) {
-          if (warp == 0) {
-            const float sc = rms_scale_smem(xs, M, ph.norm_eps, lane);
-            if (lane == 0) s_bcast = sc;
-          }
-          consumer_sync();
-          const float sc = s_bcast;
-          // rmsnorm_kernel.cu:41-45: (scale * x) * w
-          if (norm_regs) {
-#pragma unroll
-            for (int k = 0; k < kMaxNormRegs; ++k) {
-              const int i = tid + k * kConsumerThreads;
-              if (i < n4) {
-                float4 v = xs4w[i];
-                v.x = __fmul_rn(__fmul_rn(sc, v.x), nw[k].x);
-                v.y = __fmul_rn(__fmul_rn(sc, v.y), nw[k].y);
-                v.z = __fmul_rn(__fmul_rn(sc, v.z), nw[k].z);
-                v.w = __fmul_rn(__fmul_rn(sc, v.w), nw[k].w);
-                xs4w[i] = v;
-              }
-            }
-          } else {
-            for (int i = tid; i < M; i += kConsumerThreads)
-              xs[i] = __fmul_rn(__fmul_rn(sc, xs[i]), ph.norm_w[i]);
-          }
-          consumer_sync();
-        }
+        const Carry out = gemv_phase<CW, INT8, PROF>(Carry{pipe, best.v, best.i}, tok, pos, emb_row, stamp);
+        pipe = out.pipe;
+        best.v = out.best_v, best.i = out.best_i;
       }
-      const float4* xs4 = reinterpret_cast<const float4*>(xs);
-      if (stamp) stamp[1] = global_ns();
-
-      const int u0 = static_cast<int>(static_cast<long long>(cta) * ph.units / G);
-      const int u1 = static_cast<int>(static_cast<long long>(cta + 1) * ph.units / G);
-      const int rpu = ph.swiglu ? 2 : 1;
-      const int row_bytes = M * wbytes;
-      const float* residual = ph.residual_from_emb ? emb_row : ph.residual;
-
-      // bias / residual of a unit are fetched BEFORE its dot product so their L2 latency hides
-      // behind the accumulation (lane 0 only)
-      auto prefetch_addend = [&](int unit, float& bias_v, float& res_v) {
-        bias_v = 0.f, res_v = 0.f;
-        if (ph.swiglu || lane != 0) return;
-        const RowRef rr = resolve_row(ph, unit, 0);
-        if (ph.seg[rr.seg].bias != nullptr) bias_v = __ldg(ph.seg[rr.seg].bias + rr.row);
-        if (residual != nullptr) res_v = __ldcg(residual + rr.row);
-      };
-      auto epilogue = [&](int unit, float d0, float d1, float bias_v, float res_v) {
-        // lane 0 only
-        if (ph.swiglu) {
-          const float g = swiglu_ref(d0, d1);
-          if (ph.seg[0].tag_out != nullptr)
-            st_tagged_gpu(ph.seg[0].tag_out + unit, g, hand_tag(ph.hand_out));
-          else
-            ph.seg[0].out[unit] = g;
-          return;
-        }
-        if (ph.tp_out) {
-          const unsigned tag = P.tp_seq_base + static_cast<unsigned>(tok * P.exch_per_token + ph.exch) + 1u;
-          const size_t off = (static_cast<size_t>(tag & 1u) * P.tp_world + P.tp_rank) * P.tp_stride + unit;
-          for (int k = 1; k <= P.tp_world; ++k) st_tagged(P.tp_data[(P.tp_rank + k) % P.tp_world] + off, d0, tag);
-          return;
-        }
-        const RowRef rr = resolve_row(ph, unit, 0);
-        const Seg& sg = ph.seg[rr.seg];
-        float v = d0;
-        if (sg.bias != nullptr) v = __fadd_rn(v, bias_v);       // matmul.cpp:74-77: out + bias
-        if (residual != nullptr) v = __fadd_rn(res_v, v);       // llama3.cpp:683,719: x + out
-        if (sg.tag_out != nullptr) st_tagged_gpu(sg.tag_out + rr.row, v, hand_tag(ph.hand_out));
-        if (sg.out == nullptr) {
-        } else if (sg.head_major) {
-          const int hs = P.head_size;
-          sg.out[(static_cast<size_t>(rr.row / hs) * P.seq_len + pos) * hs + rr.row % hs] = v;
-        } else {
-          sg.out[static_cast<long long>(pos) * sg.pos_stride + rr.row] = v;
-        }
-        if (ph.argmax) arg_fold(best, v, rr.row);
-      };
-
-      long long cyc_wait = 0, cyc_rows = 0;
-      long long cyc4[4] = {0, 0, 0, 0};
-      if (ph.chunks_per_row == 1) {
-        const int ups = ph.rows_per_stage / rpu;
-        for (int u = u0; u < u1; u += ups) {
-          const int n = min(ups, u1 - u);
-          const long long c0 = stamp ? clock64() : 0;
-          mbar_wait(&full_bar[pipe.slot], pipe.parity);
-          const long long c1 = stamp ? clock64() : 0;
-          cyc_wait += c1 - c0;
-          const unsigned char* sbase = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
-          // units go round-robin over ALL consumer warps across stages (a stage may hold fewer
-          // units than there are warps)
-          const int first = ((warp - (u - u0)) % kConsumerWarps + kConsumerWarps) % kConsumerWarps;
-          for (int i = first; i < n; i += kConsumerWarps) {
-            const int unit = u + i;
-            float bias_v, res_v;
-            const long long t_a = stamp ? clock64() : 0;
-            prefetch_addend(unit, bias_v, res_v);
-            const long long t_b = stamp ? clock64() : 0;
-            if (P.group_size == 0) {
-              if (ph.swiglu) {
-                const float4* w[2] = {reinterpret_cast<const float4*>(sbase + static_cast<size_t>(i) * row_bytes),
-                                      reinterpret_cast<const float4*>(sbase + static_cast<size_t>(n + i) * row_bytes)};
-                float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                accum_f32<2>(w, xs4, M >> 2, lane, acc);
-                const long long t_c = stamp ? clock64() : 0;
-                const float d0 = block128_sum_vt(acc[0]);
-                const float d1 = block128_sum_vt(acc[1]);
-                const long long t_d = stamp ? clock64() : 0;
-                if (lane == 0) epilogue(unit, d0, d1, bias_v, res_v);
-                if (stamp) {
-                  cyc4[0] += t_b - t_a, cyc4[1] += t_c - t_b, cyc4[2] += t_d - t_c, cyc4[3] += clock64() - t_d;
-                }
-              } else {
-                const float4* w[1] = {reinterpret_cast<const float4*>(sbase + static_cast<size_t>(i) * row_bytes)};
-                float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
-                accum_f32<1>(w, xs4, M >> 2, lane, acc);
-                const long long t_c = stamp ? clock64() : 0;
-                const float d0 = block128_sum_vt(acc[0]);
-                const long long t_d = stamp ? clock64() : 0;
-                if (lane == 0) epilogue(unit, d0, 0.f, bias_v, res_v);
-                if (stamp) {
-                  cyc4[0] += t_b - t_a, cyc4[1] += t_c - t_b, cyc4[2] += t_d - t_c, cyc4[3] += clock64() - t_d;
-                }
-              }
-            } else {
-              if (ph.swiglu) {
-                const uint32_t* w[2];
-                const float* sc[2];
-#pragma unroll
-                for (int r = 0; r < 2; ++r) {
-                  w[r] = reinterpret_cast<const uint32_t*>(sbase + static_cast<size_t>(r * n + i) * row_bytes);
-                  sc[r] = reinterpret_cast<const float*>(sbase + ph.scale_off +
-                                                         static_cast<size_t>(r * n + i) * ph.scale_row_bytes);
-                }
-                float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                accum_w8<2>(w, sc, xs4, M, ph.group_shift, ph.group_size, lane, acc);
-                const float d0 = block128_sum_quad(acc[0]);
-                const float d1 = block128_sum_quad(acc[1]);
-                if (lane == 0) epilogue(unit, d0, d1, bias_v, res_v);
-              } else {
-                const uint32_t* w[1] = {reinterpret_cast<const uint32_t*>(sbase + static_cast<size_t>(i) * row_bytes)};
-                const float* sc[1] = {reinterpret_cast<const float*>(sbase + ph.scale_off +
-                                                                     static_cast<size_t>(i) * ph.scale_row_bytes)};
-                float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
-                accum_w8<1>(w, sc, xs4, M, ph.group_shift, ph.group_size, lane, acc);
-                const float d0 = block128_sum_quad(acc[0]);
-                if (lane == 0) epilogue(unit, d0, 0.f, bias_v, res_v);
-              }
-            }
-          }
-          __syncwarp();
-          if (stamp) cyc_rows += clock64() - c1;
-          if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
-          pipe.advance(S);
-        }
-      } else {
-        // rows longer than a stage (fp32 only): the owning warp carries its partial sums across
-        // consecutive stages; chunk boundaries are multiples of 128 packs so every virtual
-        // thread still sees its packs in increasing order.
-        for (int u = u0; u < u1; ++u) {
-          const bool mine = ((u - u0) % kConsumerWarps) == warp;
-          float bias_v = 0.f, res_v = 0.f;
-          if (mine) prefetch_addend(u, bias_v, res_v);
-          float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
-          for (int c = 0; c < ph.chunks_per_row; ++c) {
-            const int e0 = c * ph.chunk_elems;
-            const int ne = min(ph.chunk_elems, M - e0);
-            mbar_wait(&full_bar[pipe.slot], pipe.parity);
-            if (mine) {
-              const float4* w[1] = {reinterpret_cast<const float4*>(
-                  stages + static_cast<size_t>(pipe.slot) * P.stage_bytes)};
-              accum_f32<1>(w, xs4 + (e0 >> 2), ne >> 2, lane, acc);
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
-            pipe.advance(S);
-          }
-          if (mine) {
-            const float d0 = block128_sum_vt(acc[0]);
-            if (lane == 0) epilogue(u, d0, 0.f, bias_v, res_v);
-          }
-        }
-      }
-
-      if (ph.argmax) {
-        // per-CTA (max, lowest index) of the classifier rows this CTA produced
-        float bv = __shfl_sync(kFull, best.v, 0);
-        int bi = __shfl_sync(kFull, best.i, 0);
-        if (lane == 0) {
-          s_argv[warp] = bv;
-          s_argi[warp] = bi;
-        }
-        consumer_sync();
-        if (tid == 0) {
-          ArgBest b{0.f, -1};
-          for (int w = 0; w < kConsumerWarps; ++w) arg_fold(b, s_argv[w], s_argi[w]);
-          P.arg_val[cta] = b.v;
-          P.arg_idx[cta] = b.i;
-        }
-      }
-      if (stamp) {
-        stamp[2] = global_ns();
-        stamp[4] = static_cast<unsigned long long>(cyc4[0]);
-        stamp[5] = static_cast<unsigned long long>(cyc4[1]);
-        stamp[6] = static_cast<unsigned long long>(cyc4[2]);
-        stamp[7] = static_cast<unsigned long long>(cyc4[3]);
-        stamp[8] = static_cast<unsigned long long>(cyc_wait);
-        stamp[9] = static_cast<unsigned long long>(cyc_rows);
-      }
-      if (ph.barrier_after) grid_barrier(P.barrier, bar_target, G);
+      if (ph.barrier_after) grid_barrier<CT>(P.barrier, bar_target, G);
       if (stamp) stamp[3] = global_ns();
     }
 
@@ -1139,8 +1387,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
     ArgBest b{0.f, -1};
     for (int c = lane; c < G; c += 32) arg_fold(b, __ldcg(P.arg_val + c), __ldcg(P.arg_idx + c));
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1)
-      arg_fold(b, __shfl_xor_sync(kFull, b.v, off), __shfl_xor_sync(kFull, b.i, off));
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(kFull, b.v, off);
+      const int oi = __shfl_xor_sync(kFull, b.i, off);
+      arg_fold(b, ov, oi);
+    }
     const int next = b.i < 0 ? 0 : b.i;
     if (cta == 0 && tid == 0) {
       if (P.out_tokens != nullptr && step < P.max_steps) P.out_tokens[step] = next;
@@ -1164,6 +1415,17 @@ __global__ void __launch_bounds__(kThreads, 1) decode_megakernel(const Params P)
 using mega::Params;
 using mega::Phase;
 
+namespace {
+// PROF: the instantiation kllm_decoder_profile launches (its stamps cost registers in the row loops)
+template <bool PROF>
+const void* kernel_for(int consumer_warps, bool int8) {
+  if (int8)
+    return consumer_warps == 16 ? reinterpret_cast<const void*>(mega::decode_megakernel<16, true, PROF>)
+                                : reinterpret_cast<const void*>(mega::decode_megakernel<8, true, PROF>);
+  return reinterpret_cast<const void*>(mega::decode_megakernel<8, false, PROF>);
+}
+}  // namespace
+
 int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   model_ = m;
   stream_ = stream;
@@ -1174,14 +1436,19 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (!coop) return KLLM_E_UNSUPPORTED;
-  grid_ = sms;
 
   const int dim = m.dim, hid = m.hidden_dim, hs = m.head_size, kvd = m.kv_dim;
   const int q_rows = m.head_num * hs;
   const bool int8 = m.group_size > 0;
   const int wb = int8 ? 1 : 4;
-  // shapes the ring handles: 16-byte rows, 128-byte aligned kv rows (L1-cached reads stay exact)
-  if ((dim & 3) || (hid & 3) || (q_rows & 3) || (hs & 3) || hs > mega::kConsumerThreads) return KLLM_E_UNSUPPORTED;
+  // One CTA per SM, but never more CTAs than the shortest row-parallel phase has rows: the
+  // slot-reuse argument of the tagged hand-offs wants every CTA to own rows in every producing
+  // phase (a CTA without rows gates nothing and could be overtaken).  Small test shapes only.
+  grid_ = std::min(sms, std::min(dim, hid));
+  if (grid_ < m.head_num) return KLLM_E_UNSUPPORTED;  // attention: one CTA per (local) query head
+  // shapes the ring handles: 16-byte rows, 128-byte aligned kv rows (L1-cached reads stay exact);
+  // head_size <= 128: the K-tile producer issues one bulk copy per lane for hs/4 <= 32 chunk columns
+  if ((dim & 3) || (hid & 3) || (q_rows & 3) || (hs & 3) || hs > 128) return KLLM_E_UNSUPPORTED;
   if (int8 && ((dim & 15) || (hid & 15) || (q_rows & 15) || (m.group_size & 3))) return KLLM_E_UNSUPPORTED;
   if ((hs * 4) % 16 != 0) return KLLM_E_UNSUPPORTED;
   if (int8) {
@@ -1189,6 +1456,27 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
     for (int d : dims)
       if (d % m.group_size != 0 || ((d / m.group_size) * 4) % 16 != 0) return KLLM_E_UNSUPPORTED;
   }
+  // consumer warps: int8 rows are bound by instruction issue (4 instructions per weight byte), so
+  // they get 16 warps of <= 112 registers; fp32 rows by shared-memory bandwidth, 8 fat warps
+  consumer_warps_ = int8 ? 16 : 8;
+  if (const char* e = getenv("KLLM_CONSUMER_WARPS"))
+    if (int8 && (atoi(e) == 8 || atoi(e) == 16)) consumer_warps_ = atoi(e);
+  kernel_ = kernel_for<false>(consumer_warps_, int8);
+  kernel_prof_ = kernel_for<true>(consumer_warps_, int8);
+  threads_ = consumer_warps_ * 32 + 64;
+
+  // Tagged exchange instead of "write x, grid barrier, read x" after o_proj and down_proj:
+  // mandatory under tensor parallelism (it IS the all-reduce), optional on one GPU.
+  // KLLM_MEGA_TAGGED = 0: grid barriers everywhere (one GPU only); 1: tagged residual exchange;
+  // 2 (default): + tagged hand-offs q|k|v -> attention -> Wo and SwiGLU -> W2, which leaves ONE
+  // grid barrier per token (after the classifier).
+  const int W = m.tp_world > 1 ? m.tp_world : 1;
+  if (W != 1 && W != 2 && W != 4 && W != 8) return KLLM_E_UNSUPPORTED;
+  tagged_mode_ = 2;
+  if (const char* e = getenv("KLLM_MEGA_TAGGED")) tagged_mode_ = std::min(2, std::max(0, atoi(e)));
+  if (W > 1 && tagged_mode_ == 0) tagged_mode_ = 1;
+  tagged_ = tagged_mode_ >= 1;
+  const bool handoffs = tagged_mode_ >= 2;
 
   // ---- shared memory plan -----------------------------------------------------------------------
   const int max_in = std::max(std::max(dim, hid), q_rows);
@@ -1196,10 +1484,13 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   const int attn_ws = 2 * hs * 4;
   xbuf = std::max(xbuf, attn_ws);
   xbuf = (xbuf + 127) & ~127;
-  const int budget = max_smem - xbuf - 2048;  // static smem + slack
-  const int min_row = std::min(std::min(dim, hid), q_rows) * wb;
-  (void)min_row;
-  int stage_bytes = 32 * 1024;
+  const int xres = tagged_ ? ((dim * 4 + 127) & ~127) : 0;  // the CTA's copy of the residual stream
+  const int budget = max_smem - mega::kCtlBytes - xbuf - xres - 256;  // control block + slack
+  // Stage size: whole rows, so pick it to waste little of the ring on the model's row lengths.
+  // fp32: 32 KB (4 rows of dim 2048, 2 of 4096).  int8: 27 KB = 6 rows of dim 4096 (+ scales) or
+  // 2 rows of hidden 11008, which leaves six stages next to the 44 KB input vector and the 16 KB
+  // residual stream of Llama-2-7B.
+  int stage_bytes = int8 ? 27 * 1024 : 32 * 1024;
   if (const char* e = getenv("KLLM_STAGE_BYTES")) stage_bytes = atoi(e);
   stage_bytes = (stage_bytes + 127) & ~127;
   int stages = budget / stage_bytes;
@@ -1208,10 +1499,11 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   if (stages < 2) return KLLM_E_UNSUPPORTED;
   stage_bytes_ = stage_bytes;
   stages_ = stages;
-  attn_tile_ = std::min(stage_bytes / (hs * 4), mega::kConsumerThreads) & ~31;
+  attn_tile_ = std::min(stage_bytes / (hs * 4), mega::kSoftmaxThreads) & ~31;
   if (attn_tile_ < 32) return KLLM_E_UNSUPPORTED;
   xbuf_bytes_ = xbuf;
-  smem_bytes_ = static_cast<size_t>(xbuf) + static_cast<size_t>(stages) * stage_bytes;
+  xres_bytes_ = xres;
+  smem_bytes_ = static_cast<size_t>(mega::kCtlBytes) + xbuf + xres + static_cast<size_t>(stages) * stage_bytes;
 
   // ---- phase table ---------------------------------------------------------------------------------
   std::vector<Phase> ph;
@@ -1256,17 +1548,6 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
     return 0;
   };
 
-  // Tagged exchange instead of "write x, grid barrier, read x" after o_proj and down_proj:
-  // mandatory under tensor parallelism (it IS the all-reduce), optional on one GPU.
-  // KLLM_MEGA_TAGGED = 0: grid barriers everywhere (one GPU only); 1: tagged residual exchange;
-  // 2 (default): + tagged hand-offs q|k|v -> attention -> Wo and SwiGLU -> W2, which leaves ONE
-  // grid barrier per token (after the classifier).
-  const int W = m.tp_world > 1 ? m.tp_world : 1;
-  tagged_mode_ = 2;
-  if (const char* e = getenv("KLLM_MEGA_TAGGED")) tagged_mode_ = std::min(2, std::max(0, atoi(e)));
-  if (W > 1 && tagged_mode_ == 0) tagged_mode_ = 1;
-  tagged_ = tagged_mode_ >= 1;
-  const bool handoffs = tagged_mode_ >= 2;
   unsigned long long *t_q = nullptr, *t_k = nullptr, *t_v = nullptr, *t_attn = nullptr, *t_h = nullptr;
   if (handoffs) {
     const size_t words = static_cast<size_t>(2 * q_rows + 2 * kvd + hid);
@@ -1276,23 +1557,19 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
     t_q = d_handoff_, t_k = t_q + q_rows, t_v = t_k + kvd, t_attn = t_v + kvd, t_h = t_attn + q_rows;
   }
   int hands = 0;
-  if (tagged_) {
-    if (cudaMalloc(&d_xbuf_, sizeof(float) * 2 * dim) != cudaSuccess) return static_cast<int>(cudaErrorMemoryAllocation);
-    cudaMemsetAsync(d_xbuf_, 0, sizeof(float) * 2 * dim, stream);
-    if (W == 1) {
-      if (cudaMalloc(&d_tagged_, sizeof(unsigned long long) * 2 * dim) != cudaSuccess)
-        return static_cast<int>(cudaErrorMemoryAllocation);
-      cudaMemsetAsync(d_tagged_, 0, sizeof(unsigned long long) * 2 * dim, stream);
-    }
+  if (tagged_ && W == 1) {
+    if (cudaMalloc(&d_tagged_, sizeof(unsigned long long) * 2 * dim) != cudaSuccess)
+      return static_cast<int>(cudaErrorMemoryAllocation);
+    cudaMemsetAsync(d_tagged_, 0, sizeof(unsigned long long) * 2 * dim, stream);
   }
-  auto xbuf_of = [&](int e) { return d_xbuf_ + static_cast<size_t>(e & 1) * dim; };
   int exch = 0, bars = 0;
   auto close_phase = [&](Phase& p, bool barrier) {
     p.barrier_after = barrier ? 1 : 0;
     if (barrier) ++bars;
     p.barrier_idx = bars;
   };
-  // a phase whose input is the residual stream: tagged -> x_old + partials of the last exchange
+  // a phase whose input is the residual stream: tagged -> x_old (shared memory) + partials of the
+  // last exchange
   auto input_is_x = [&](Phase& p) {
     if (!tagged_ || exch == 0) {
       p.x = m.x;
@@ -1300,8 +1577,6 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
     }
     p.tp_in = 1;
     p.exch = exch - 1;
-    p.x_old = exch >= 2 ? xbuf_of(exch - 2) : nullptr;  // nullptr: the embedding row
-    p.x_new = xbuf_of(exch - 1);
     p.x = nullptr;
   };
   // a row-parallel matmul whose output is added to the residual stream
@@ -1446,13 +1721,13 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
     return static_cast<int>(cudaErrorMemoryAllocation);
   cudaStreamSynchronize(stream);  // ph (host vector) must outlive the async copy
 
-  cudaError_t e = cudaFuncSetAttribute(mega::decode_megakernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t e = cudaFuncSetAttribute(kernel_, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        static_cast<int>(smem_bytes_));
   if (e != cudaSuccess) return static_cast<int>(e);
+  e = cudaFuncSetAttribute(kernel_prof_, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_bytes_));
+  if (e != cudaSuccess) return static_cast<int>(e);
   int occ = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mega::decode_megakernel, mega::kThreads,
-                                                    smem_bytes_);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel_, threads_, smem_bytes_);
   if (e != cudaSuccess) return static_cast<int>(e);
   if (occ < 1) return KLLM_E_UNSUPPORTED;
   barrier_base_ = 0;
@@ -1465,11 +1740,9 @@ void MegaEngine::destroy() {
   if (d_barrier_) cudaFree(d_barrier_);
   if (d_arg_val_) cudaFree(d_arg_val_);
   if (d_arg_idx_) cudaFree(d_arg_idx_);
-  if (d_xbuf_) cudaFree(d_xbuf_);
   if (d_tagged_) cudaFree(d_tagged_);
   if (d_handoff_) cudaFree(d_handoff_);
   d_handoff_ = nullptr;
-  d_xbuf_ = nullptr;
   d_tagged_ = nullptr;
   d_phases_ = nullptr;
   d_barrier_ = nullptr;
@@ -1489,6 +1762,7 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
   P.num_stages = stages_;
   P.stage_bytes = stage_bytes_;
   P.xbuf_bytes = xbuf_bytes_;
+  P.xres_bytes = xres_bytes_;
   P.attn_tile = attn_tile_;
   P.pf_stages = 8;  // 8 x 32 KB x 148 SMs = 38 MB of weights in flight towards L2 (measured: 6-12 best, >=24 thrashes L2)
   if (const char* e = getenv("KLLM_PREFETCH_STAGES")) P.pf_stages = std::max(0, atoi(e));
@@ -1531,9 +1805,8 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
   P.prof = prof_dev;
   P.prof_token = prof_token;
   void* args[] = {&P};
-  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(mega::decode_megakernel),
-                                              dim3(grid_), dim3(mega::kThreads), args, smem_bytes_,
-                                              stream_);
+  cudaError_t e = cudaLaunchCooperativeKernel(const_cast<void*>(prof_dev != nullptr ? kernel_prof_ : kernel_), dim3(grid_), dim3(threads_), args,
+                                              smem_bytes_, stream_);
   if (e != cudaSuccess) return static_cast<int>(e);
   tp_seq_base_ += static_cast<unsigned>(n_tokens) * static_cast<unsigned>(exch_per_token_);
   hand_base_ += static_cast<unsigned>(n_tokens) * static_cast<unsigned>(hands_per_token_);

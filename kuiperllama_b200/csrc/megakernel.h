@@ -50,13 +50,13 @@ struct Phase {
   //   tp_out: each produced row is published as {value, tag} -- one 64-bit store -- into every
   //           rank's exchange area instead of seg[0].out; no residual add, no barrier after.
   //   tp_in : the input vector is x_old + (p_0 + p_1 + ... + p_{world-1}), p_r = rank r's tagged
-  //           partials of exchange `exch`, polled until their tag is current; the CTA's slice of
-  //           the result is kept in x_new as the next exchange's x_old.
+  //           partials of exchange `exch`, polled until their tag is current; x_old is the CTA's
+  //           own shared-memory copy of the residual stream (it starts as the embedding row of the
+  //           token and is updated by every exchange), so the stream never round-trips through
+  //           global memory between CTAs.
   int tp_in, tp_out, exch;
   int barrier_after;      // 1: a grid barrier closes the phase
   int barrier_idx;        // barriers of this token passed once this phase is closed
-  const float* x_old;     // tp_in: residual stream before the exchange (nullptr: the embedding row)
-  float* x_new;           // tp_in: residual stream after it
   // Local tagged hand-offs (same words, one rank): the phase's input vector is polled from tag_in
   // (GEMV) or tq/tk/tv (attention: this head's query, its kv head's raw key and value rows);
   // outputs go to seg[].tag_out (GEMV) or ta (attention).  hand_in / hand_out number the
@@ -78,6 +78,7 @@ struct Params {
   const Phase* phases;
   int n_phases, n_tokens;
   int num_stages, stage_bytes, xbuf_bytes;
+  int xres_bytes;  // shared-memory copy of the residual stream behind the input vector (tagged modes; else 0)
   int attn_tile;  // timesteps per K/V ring stage
   int pf_stages;  // L2 prefetch run-ahead of the ring producer, in ring stages (0 = off)
   int group_size;
@@ -158,6 +159,7 @@ class MegaEngine {
   int stage_bytes() const { return stage_bytes_; }
   int phases() const { return n_phases_; }
   int attn_tile() const { return attn_tile_; }
+  int consumer_warps() const { return consumer_warps_; }
 
  private:
   MegaModel model_{};
@@ -166,14 +168,16 @@ class MegaEngine {
   void* d_barrier_ = nullptr;
   void* d_arg_val_ = nullptr;
   void* d_arg_idx_ = nullptr;
-  float* d_xbuf_ = nullptr;                // [2][dim]: the residual stream, alternating per exchange
   unsigned long long* d_tagged_ = nullptr;  // single-GPU exchange area (tp_world == 1)
   unsigned long long* d_handoff_ = nullptr;  // local tagged hand-off vectors (q | k | v | attn | h)
   bool tagged_ = false;
   int tagged_mode_ = 0;  // 0: grid barriers everywhere; 1: tagged residual exchange; 2: + tagged hand-offs
   int exch_per_token_ = 0, hands_per_token_ = 0;
   unsigned tp_seq_base_ = 0, hand_base_ = 0;
-  int grid_ = 0, stages_ = 0, stage_bytes_ = 0, xbuf_bytes_ = 0, n_phases_ = 0, attn_tile_ = 0;
+  int grid_ = 0, stages_ = 0, stage_bytes_ = 0, xbuf_bytes_ = 0, xres_bytes_ = 0, n_phases_ = 0, attn_tile_ = 0;
+  int consumer_warps_ = 8, threads_ = 0;
+  const void* kernel_ = nullptr;       // decode_megakernel<consumer warps, int8, false>
+  const void* kernel_prof_ = nullptr;  // ... <.., true>: records the phase timeline stamps
   int n_barriers_per_token_ = 0;
   size_t smem_bytes_ = 0;
   unsigned barrier_base_ = 0;
