@@ -128,6 +128,17 @@ typedef struct {
 
 int kllm_gemv_fused(const kllm_gemv_job* job, void* stream);
 
+/* ---- batched prompt GEMM on the tcgen05 tensor cores (TOLERANCED: TF32 multiply, fp32 accumulate) ----
+ * out[n_tokens, out_dim] = x[n_tokens, in_dim] . w[out_dim, in_dim]^T, all fp32 row-major device memory.
+ * Replaces the n_tokens single-row GEMVs the reference issues for a prompt, one full forward per
+ * prompt token (demo/main.cpp:18-23 -> LLama2Model::predict, llama3.cpp:147-167; MatmulLayer::forward,
+ * matmul.cpp:57-80): the weight matrix is streamed once per 256 tokens instead of once per token.
+ * TMA tensor-map loads (cp.async.bulk.tensor, 128-byte swizzle) feed tcgen05.mma.kind::tf32 with the
+ * accumulator in TMEM.  Results agree with the fp32 GEMV to ~1e-3 relative (10-bit mantissas), NOT
+ * bit for bit: the decode path never uses it.  in_dim % 4 == 0, 16-byte aligned x and w. */
+int kllm_gemm_tf32(const float* x, const float* w, float* out, int n_tokens, int in_dim, int out_dim,
+                   void* stream);
+
 /* ---- tensor-parallel exchange --------------------------------------------------------------
  * Not in the reference (single GPU: llama3.cpp:118 pins device 0); SURVEY.md section 8e.  One
  * process per GPU; each owns a kllm_comm.  The decoder issues exactly two all-reduces per layer:
@@ -206,6 +217,22 @@ void kllm_decoder_destroy(kllm_decoder* dec);
 int kllm_decoder_step(kllm_decoder* dec, int32_t token_host, int32_t pos, int is_prompt,
                       int32_t* next_host);
 
+/* The whole prompt in one call: positions start_pos .. start_pos + n_tokens - 1 take tokens_host[i] as
+ * input, fill the KV cache, and *next_host is the greedy id after the LAST prompt token (what
+ * demo/main.cpp:18-41 obtains by calling predict() once per prompt position with is_prompt = true and
+ * discarding every result but the last).  Persistent engine: one launch, and the classifier pass --
+ * which the reference runs and throws away for every prompt position (llama3.cpp:642-650, 738-739) --
+ * is skipped for all but the last position.  Bit-identical KV cache and next id to stepping. */
+int kllm_decoder_prompt(kllm_decoder* dec, const int32_t* tokens_host, int32_t n_tokens, int32_t start_pos,
+                        int32_t* next_host);
+/* TOLERANCED batched prefill: the same contract as kllm_decoder_prompt, but the prompt positions go
+ * through every layer together -- each projection one GEMM [n, in] x [out, in]^T on the tcgen05
+ * tensor cores (TF32 multiply, fp32 accumulate, kllm_gemm_tf32), the weights streamed once per 256
+ * positions instead of once per position; classifier only for the last position.  KV-cache rows and
+ * logits agree with the position-by-position path to ~1e-3 relative, NOT bit for bit (TF32 keeps 10
+ * mantissa bits).  fp32 checkpoints on one GPU; KLLM_E_UNSUPPORTED otherwise (use kllm_decoder_prompt). */
+int kllm_decoder_prefill_tf32(kllm_decoder* dec, const int32_t* tokens_host, int32_t n_tokens, int32_t start_pos,
+                              int32_t* next_host);
 /* Device-resident greedy loop: positions start_pos .. start_pos+n_steps-1, each step feeding
  * the previous argmax back without leaving the GPU; ids copied to out_tokens_host at the end
  * (one synchronisation).  teacher_host (optional, n_steps ids) forces the inputs instead. */

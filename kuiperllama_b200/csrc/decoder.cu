@@ -17,6 +17,7 @@
 // argmax_kernel.cu:73-87).  Buffer roles follow llama3.cpp:425-500.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -124,6 +125,9 @@ struct kllm_decoder {
   cudaGraph_t graph_tf = nullptr;
   cudaGraphExec_t exec_tf = nullptr;    // teacher forced
   int launches_per_step = 0;
+  // batched tcgen05 prefill (kllm_decoder_prefill_tf32): activations of one block of prompt positions
+  float* pf_buf = nullptr;
+  PrefillWorkspace pf_ws{};
 };
 
 namespace {
@@ -417,6 +421,7 @@ void kllm_decoder_destroy(kllm_decoder* dc) {
   if (dc->st) cudaFree(dc->st);
   if (dc->out_tokens) cudaFree(dc->out_tokens);
   if (dc->teacher) cudaFree(dc->teacher);
+  if (dc->pf_buf) cudaFree(dc->pf_buf);
   if (dc->st_host) cudaFreeHost(dc->st_host);
   if (dc->io_host) cudaFreeHost(dc->io_host);
   if (dc->own_stream && dc->stream) cudaStreamDestroy(dc->stream);
@@ -434,7 +439,8 @@ int kllm_decoder_step(kllm_decoder* dc, int32_t token_host, int32_t pos, int is_
   hs->next = -1;
   KLLM_TRY(cudaMemcpyAsync(dc->st, hs, sizeof(StepState), cudaMemcpyHostToDevice, dc->stream));
   if (dc->use_mega) {
-    KLLM_TRY(dc->mega.run(1, nullptr));
+    // a prompt position needs no logits (llama3.cpp:738-739 returns -1): the classifier is skipped
+    KLLM_TRY(dc->mega.run(1, nullptr, nullptr, -1, is_prompt ? 1 : 0));
   } else {
     KLLM_TRY(cudaGraphLaunch(dc->exec, dc->stream));
     count_launch(static_cast<uint64_t>(dc->launches_per_step));
@@ -442,6 +448,104 @@ int kllm_decoder_step(kllm_decoder* dc, int32_t token_host, int32_t pos, int is_
   KLLM_TRY(cudaMemcpyAsync(hs, dc->st, sizeof(StepState), cudaMemcpyDeviceToHost, dc->stream));
   KLLM_TRY(cudaStreamSynchronize(dc->stream));
   *next_host = is_prompt ? -1 : hs->next;
+  return 0;
+}
+
+int kllm_decoder_prompt(kllm_decoder* dc, const int32_t* tokens_host, int32_t n_tokens, int32_t start_pos,
+                        int32_t* next_host) {
+  if (!dc || !tokens_host || !next_host || n_tokens <= 0 || start_pos < 0) return KLLM_E_INVALID;
+  if (start_pos + n_tokens > dc->d.seq_len) return KLLM_E_INVALID;
+  StepState* hs = dc->st_host;
+  hs->token = tokens_host[0];
+  hs->pos = start_pos;
+  hs->step = 0;
+  hs->next = -1;
+  KLLM_TRY(cudaMemcpyAsync(dc->st, hs, sizeof(StepState), cudaMemcpyHostToDevice, dc->stream));
+  std::memcpy(dc->io_host, tokens_host, sizeof(int32_t) * n_tokens);
+  KLLM_TRY(cudaMemcpyAsync(dc->teacher, dc->io_host, sizeof(int32_t) * n_tokens, cudaMemcpyHostToDevice,
+                           dc->stream));
+  if (dc->use_mega) {
+    // ONE launch for the whole prompt; only the last position runs the classifier
+    KLLM_TRY(dc->mega.run(n_tokens, dc->teacher, nullptr, -1, n_tokens - 1));
+  } else {
+    for (int i = 0; i < n_tokens; ++i) KLLM_TRY(cudaGraphLaunch(dc->exec_tf, dc->stream));
+    count_launch(static_cast<uint64_t>(dc->launches_per_step) * n_tokens);
+  }
+  KLLM_TRY(cudaMemcpyAsync(hs, dc->st, sizeof(StepState), cudaMemcpyDeviceToHost, dc->stream));
+  KLLM_TRY(cudaStreamSynchronize(dc->stream));
+  *next_host = hs->next;
+  return 0;
+}
+
+int kllm_decoder_prefill_tf32(kllm_decoder* dc, const int32_t* tokens_host, int32_t n_tokens, int32_t start_pos,
+                              int32_t* next_host) {
+  if (!dc || !tokens_host || !next_host || n_tokens <= 0 || start_pos < 0) return KLLM_E_INVALID;
+  const kllm_decoder_desc& d = dc->d;
+  if (start_pos + n_tokens > d.seq_len) return KLLM_E_INVALID;
+  if (d.group_size != 0 || d.tp_size > 1) return KLLM_E_UNSUPPORTED;  // fp32 checkpoints, one GPU
+  constexpr int kBlock = 256;  // prompt positions per pass = the N of the tcgen05.mma
+  const int hs = dc->head_size, q_rows = d.head_num * hs, kvd = dc->kv_dim;
+  if ((d.dim & 3) || (d.hidden_dim & 3) || (q_rows & 3)) return KLLM_E_UNSUPPORTED;
+  if (dc->pf_buf == nullptr) {
+    const size_t per_row = static_cast<size_t>(3 * d.dim + 2 * q_rows + 2 * kvd + 2 * d.hidden_dim);
+    if (cudaMalloc(&dc->pf_buf, per_row * kBlock * sizeof(float)) != cudaSuccess)
+      return static_cast<int>(cudaErrorMemoryAllocation);
+    float* p = dc->pf_buf;
+    auto take = [&](size_t n) {
+      float* r = p;
+      p += n * kBlock;
+      return r;
+    };
+    dc->pf_ws.x = take(d.dim), dc->pf_ws.xn = take(d.dim), dc->pf_ws.tmp = take(d.dim);
+    dc->pf_ws.q = take(q_rows), dc->pf_ws.att = take(q_rows);
+    dc->pf_ws.k = take(kvd), dc->pf_ws.v = take(kvd);
+    dc->pf_ws.h1 = take(d.hidden_dim), dc->pf_ws.h3 = take(d.hidden_dim);
+  }
+  KLLM_TRY(prefill_attention_smem_opt_in(static_cast<size_t>(start_pos + n_tokens) * sizeof(float)));
+  PrefillModel m{};
+  m.dim = d.dim, m.hidden_dim = d.hidden_dim, m.layer_num = d.layer_num, m.head_num = d.head_num;
+  m.kv_head_num = d.kv_head_num, m.vocab_size = d.vocab_size, m.seq_len = d.seq_len, m.head_size = hs;
+  m.flavour = d.flavour, m.mega_layout = dc->use_mega ? 1 : 0, m.eps = flavour_eps(d.flavour);
+  m.tok_emb = d.tok_emb, m.attn_norm = dc->attn_norm.data(), m.ffn_norm = dc->ffn_norm.data();
+  m.wq = dc->wq.data(), m.wk = dc->wk.data(), m.wv = dc->wv.data(), m.wo = dc->wo.data();
+  m.w1 = dc->w1.data(), m.w2 = dc->w2.data(), m.w3 = dc->w3.data();
+  m.bq = dc->bq.empty() ? nullptr : dc->bq.data();
+  m.bk = dc->bk.empty() ? nullptr : dc->bk.data();
+  m.bv = dc->bv.empty() ? nullptr : dc->bv.data();
+  m.key_cache = dc->kcache, m.value_cache = dc->vcache, m.sin_cache = dc->sin_t, m.cos_cache = dc->cos_t;
+
+  std::memcpy(dc->io_host, tokens_host, sizeof(int32_t) * n_tokens);
+  KLLM_TRY(cudaMemcpyAsync(dc->teacher, dc->io_host, sizeof(int32_t) * n_tokens, cudaMemcpyHostToDevice, dc->stream));
+  int last_rows = 0;
+  for (int c0 = 0; c0 < n_tokens; c0 += kBlock) {
+    const int T = std::min(kBlock, n_tokens - c0);
+    KLLM_TRY(prefill_block(m, dc->pf_ws, dc->teacher + c0, T, start_pos + c0, dc->stream));
+    last_rows = T;
+  }
+  // last prompt position only: final RMSNorm + classifier (cls_logits, llama3.cpp:722-731) and the
+  // greedy id (post_processing, :733-745) through the decode path's fused GEMV and argmax
+  StepState* hs_state = dc->st_host;
+  hs_state->token = tokens_host[n_tokens - 1];
+  hs_state->pos = start_pos + n_tokens - 1;
+  hs_state->step = 0;
+  hs_state->next = -1;
+  KLLM_TRY(cudaMemcpyAsync(dc->st, hs_state, sizeof(StepState), cudaMemcpyHostToDevice, dc->stream));
+  {
+    kllm_gemv_job j{};
+    j.x = dc->pf_ws.x + static_cast<size_t>(last_rows - 1) * d.dim;
+    j.norm_w = d.final_norm;
+    j.norm_eps = flavour_eps(d.flavour);
+    j.in_dim = d.dim;
+    j.n_seg = 1;
+    j.seg[0] = {d.wcls, nullptr, nullptr, dc->logits, d.vocab_size};
+    KLLM_TRY(gemv_dispatch(&j, GemvExtra{}, dc->stream));
+  }
+  argmax_advance_kernel<<<1, 1024, 0, dc->stream>>>(dc->logits, d.vocab_size, dc->st, nullptr, nullptr, d.seq_len);
+  count_launch();
+  KLLM_TRY(cudaGetLastError());
+  KLLM_TRY(cudaMemcpyAsync(hs_state, dc->st, sizeof(StepState), cudaMemcpyDeviceToHost, dc->stream));
+  KLLM_TRY(cudaStreamSynchronize(dc->stream));
+  *next_host = hs_state->next;
   return 0;
 }
 

@@ -38,5 +38,26 @@ int launch_mha(PosArg pos, int head_num, int layer_index, int seq_len, int kv_di
 // tp_comm.cu: exchange areas [2][world][stride] of 64-bit tagged words, one per rank (peer transport)
 int comm_tagged_areas(kllm_comm* comm, unsigned long long** areas8, int* world, int* rank, int* stride);
 
+// prefill.cu: one block of T prompt positions through every layer with batched tcgen05 GEMMs
+struct PrefillModel {
+  int dim, hidden_dim, layer_num, head_num, kv_head_num, vocab_size, seq_len, head_size, flavour;
+  int mega_layout;  // 1: the persistent engine's head-major K / V cache layout (megakernel.cu)
+  float eps;
+  const float* tok_emb;
+  const float* const* attn_norm;
+  const float* const* ffn_norm;
+  const void* const* wq; const void* const* wk; const void* const* wv; const void* const* wo;
+  const void* const* w1; const void* const* w2; const void* const* w3;
+  const float* const* bq; const float* const* bk; const float* const* bv;
+  float* key_cache; float* value_cache;
+  const float* sin_cache; const float* cos_cache;
+};
+struct PrefillWorkspace {  // [block, .] activations
+  float *x, *xn, *q, *k, *v, *att, *h1, *h3, *tmp;
+};
+int prefill_block(const PrefillModel& m, PrefillWorkspace& ws, const int32_t* tokens_dev, int T, int start_pos,
+                  cudaStream_t stream);
+int prefill_attention_smem_opt_in(size_t bytes);
+
 inline float flavour_eps(int flavour) { return flavour == KLLM_FLAVOUR_QWEN2 ? 1e-6f : 1e-5f; }
 }  // namespace kllm

@@ -53,6 +53,14 @@
 namespace kllm {
 namespace mega {
 
+// The phase bodies are written as functions but inlined: real calls make ptxas spill around them,
+// and with the ring taking all of shared memory there is no L1 left -- a spill is an L2 round trip.
+#ifndef KLLM_PHASE_CALL
+#define KLLM_PHASE_CALL __forceinline__
+#endif
+#ifndef KLLM_STAGE_CALL
+#define KLLM_STAGE_CALL __noinline__  // once per phase, and their poll buffers would otherwise push the row loops' state out
+#endif
 constexpr int kMaxStages = 16;
 constexpr int kMaxWarps = 16;
 constexpr int kSoftmaxThreads = 256;  // mha_kernel.cu:112-127 launches 256 threads per head
@@ -191,26 +199,23 @@ struct Pipe {
   }
 };
 
-// Control block at the start of dynamic shared memory.  The ring leaves only a few KB of L1, so
-// everything the inner loops touch lives in shared memory or registers: the schedule entries the
-// consumers, the ring producer and the L2 prefetcher are working on (usually three different
-// phases) and a copy of the kernel parameters for the phase functions, which are real calls
-// (__noinline__): inlined into one huge kernel their row loops inherit its register pressure and
-// ptxas serialises every shared-memory load with its math.
-struct Ctl {
-  uint64_t full_bar[kMaxStages];
-  uint64_t empty_bar[kMaxStages];
-  float s_warp[kMaxWarps];
-  float s_argv[kMaxWarps];
-  int s_argi[kMaxWarps];
-  float s_bcast;
-  volatile unsigned fill_count;  // ring stages the producer has issued so far
-  Phase ph_cons, ph_prod, ph_pf;
-  Params P;
-};
-constexpr int kCtlBytes = (static_cast<int>(sizeof(Ctl)) + 127) & ~127;
+// Static shared memory (namespace scope, so the phase functions address it with immediates instead of
+// pointers held in registers).  The ring leaves only a few KB of L1, so everything the inner loops
+// touch lives in shared memory or registers: the schedule entries the consumers, the ring producer
+// and the L2 prefetcher are working on (usually three different phases), the barriers and the
+// reduction scratch.
+__shared__ uint64_t g_full_bar[kMaxStages];
+__shared__ uint64_t g_empty_bar[kMaxStages];
+__shared__ float g_s_warp[kMaxWarps];
+__shared__ float g_s_argv[kMaxWarps];
+__shared__ int g_s_argi[kMaxWarps];
+__shared__ float g_s_bcast;
+__shared__ volatile unsigned g_fill_count;  // ring stages the producer has issued so far
+__shared__ Phase g_ph_cons;
+__shared__ Phase g_ph_prod;
+__shared__ Phase g_ph_pf;
+constexpr int kCtlBytes = 0;
 extern __shared__ __align__(128) unsigned char smem[];
-__device__ __forceinline__ Ctl& ctl() { return *reinterpret_cast<Ctl*>(smem); }
 // per-thread state the phase functions hand back to the kernel loop
 struct Carry {
   Pipe pipe;
@@ -276,17 +281,17 @@ __device__ __forceinline__ int run_length(const RowRef& rr, int lane, int nrows)
 // a batch of loads first, then the math that consumes them.
 __device__ __forceinline__ float4 lds_f4(uint32_t a) {
   float4 v;
-  asm volatile("ld.volatile.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
   return v;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
   uint32_t v;
-  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
 __device__ __forceinline__ float lds_f32(uint32_t a) {
   float v;
-  asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
   return v;
 }
 
@@ -294,50 +299,33 @@ __device__ __forceinline__ float lds_f32(uint32_t a) {
 // NR rows of a task share each load of x; per batch (two 32-pack columns) 2 x loads and 2 NR weight
 // loads are issued before the 2 NR independent dot4 chains.
 template <int NR>
-struct ColF32 {  // one 32-pack column of a task: the lane's pack of x and of each of the NR rows
-  float4 x;
-  float4 w[NR];
-};
-template <int NR>
-__device__ __forceinline__ void load_col(ColF32<NR>& c, uint32_t xp, const uint32_t (&wp)[NR], uint32_t off) {
-  c.x = lds_f4(xp + off);
-#pragma unroll
-  for (int r = 0; r < NR; ++r) c.w[r] = lds_f4(wp[r] + off);
-}
-template <int NR, int J>
-__device__ __forceinline__ void fold_col(const ColF32<NR>& c, float (&acc)[NR][4]) {
-#pragma unroll
-  for (int r = 0; r < NR; ++r) acc[r][J] = __fadd_rn(dot4_ref(c.x, c.w[r]), acc[r][J]);
-}
-template <int NR>
 __device__ __forceinline__ void accum_f32(const uint32_t (&w)[NR], uint32_t x, int n_packs, int lane,
                                           float (&acc)[NR][4]) {
-  const int blocks = n_packs >> 7;  // full 128-pack blocks = 4 columns of 32 packs
+  // Full 128-pack blocks run branch-free with all 4 * (1 + NR) shared loads issued before the math
+  // (two blocks in flight), so the four independent chains per row overlap the LDS latency.
+  const int full = n_packs & ~127;
   uint32_t xp = x + lane * 16;
   uint32_t wp[NR];
 #pragma unroll
   for (int r = 0; r < NR; ++r) wp[r] = w[r] + lane * 16;
-  // Software pipeline over the columns with two register buffers: the 1 + NR loads of the next
-  // column are in flight while the NR dot4 chains of the current one run.
-  if (blocks > 0) {
-    ColF32<NR> a, b;
-    load_col<NR>(a, xp, wp, 0);
-#pragma unroll 1
-    for (int blk = 0; blk < blocks; ++blk) {
-      load_col<NR>(b, xp, wp, 512);
-      fold_col<NR, 0>(a, acc);
-      load_col<NR>(a, xp, wp, 1024);
-      fold_col<NR, 1>(b, acc);
-      load_col<NR>(b, xp, wp, 1536);
-      fold_col<NR, 2>(a, acc);
-      xp += 2048;
+#pragma unroll 2
+  for (int base = 0; base < full; base += 128) {
+    float4 xv[4];
+    float4 wv[NR][4];
 #pragma unroll
-      for (int r = 0; r < NR; ++r) wp[r] += 2048;
-      if (blk + 1 < blocks) load_col<NR>(a, xp, wp, 0);
-      fold_col<NR, 3>(b, acc);
-    }
+    for (int j = 0; j < 4; ++j) xv[j] = lds_f4(xp + 512 * j);
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wv[r][j] = lds_f4(wp[r] + 512 * j);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int r = 0; r < NR; ++r) acc[r][j] = __fadd_rn(dot4_ref(xv[j], wv[r][j]), acc[r][j]);
+    xp += 2048;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) wp[r] += 2048;
   }
-  const int full = blocks << 7;
   if (full < n_packs) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -505,16 +493,15 @@ __device__ __forceinline__ void arg_fold(ArgBest& a, float ov, int oi) {
 __device__ __forceinline__ int attn_tiles(int pos, int T) { return (pos + T - 1) / T; }
 
 template <int CW>
-__device__ __noinline__ Pipe attention_phase(int head, int pos, Pipe pipe, unsigned tag_in, unsigned tag_out) {
-  Ctl& c = ctl();
-  const Params& P = c.P;
-  const Phase& ph = c.ph_cons;
-  float* ws = reinterpret_cast<float*>(smem + kCtlBytes);
-  float* s_warp = c.s_warp;
-  float* s_bcast = &c.s_bcast;
-  unsigned char* stages = smem + kCtlBytes + P.xbuf_bytes + P.xres_bytes;
-  uint64_t* full_bar = c.full_bar;
-  uint64_t* empty_bar = c.empty_bar;
+__device__ KLLM_PHASE_CALL Pipe attention_phase(const Params& P, int head, int pos, Pipe pipe, unsigned tag_in,
+                                                 unsigned tag_out) {
+  const Phase& ph = g_ph_cons;
+  float* ws = reinterpret_cast<float*>(smem);
+  float* s_warp = g_s_warp;
+  float* s_bcast = &g_s_bcast;
+  unsigned char* stages = smem + P.xbuf_bytes + P.xres_bytes;
+  uint64_t* full_bar = g_full_bar;
+  uint64_t* empty_bar = g_empty_bar;
   constexpr int CT = CW * 32;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
@@ -607,41 +594,53 @@ __device__ __noinline__ Pipe attention_phase(int head, int pos, Pipe pipe, unsig
   }
   consumer_sync<CT>();
 
-  // ---- softmax, mha_kernel.cu:7-45: 256 strided threads + cub<256> block-reduce order (the first
-  // 256 consumer threads play them; any further warps only keep the barriers) --------------------
+  // ---- softmax, mha_kernel.cu:7-45: the reference runs 256 strided threads and cub<256> block
+  // reductions.  Here 128 threads play two virtual threads each (v = tid and v = tid + 128, i.e.
+  // elements tid + 256 k and tid + 128 + 256 k): the maximum does not care about order, and for the
+  // sum each virtual thread keeps its own left-to-right partial, each virtual warp its own shuffle
+  // tree (real warp q holds virtual warps q and q + 4), then the eight warp sums are added in order.
   const int size = pos + 1;
-  const bool sm_thread = tid < kSoftmaxThreads;
-  constexpr int kSmWarps = kSoftmaxThreads / 32;
-  float max_val = (sm_thread && tid < size) ? score_head[tid] : -FLT_MAX;
+  constexpr int kHalf = kSoftmaxThreads / 2;  // 128 real threads
+  static_assert(CT >= kHalf, "softmax needs 128 consumer threads");
+  const bool sm_thread = tid < kHalf;
+  float max_val = -FLT_MAX;
   if (sm_thread)
-    for (int i = tid + kSoftmaxThreads; i < size; i += kSoftmaxThreads) max_val = fmaxf(max_val, score_head[i]);
+    for (int i = tid; i < size; i += kHalf) max_val = fmaxf(max_val, score_head[i]);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) max_val = fmaxf(max_val, __shfl_xor_sync(kFull, max_val, off));
   if (lane == 0 && sm_thread) s_warp[warp] = max_val;
   consumer_sync<CT>();
-  max_val = s_warp[0];
-#pragma unroll
-  for (int w = 1; w < kSmWarps; ++w) max_val = fmaxf(max_val, s_warp[w]);
+  max_val = fmaxf(fmaxf(s_warp[0], s_warp[1]), fmaxf(s_warp[2], s_warp[3]));
   consumer_sync<CT>();
 
-  float sum = 0.0f;
-  if (sm_thread)
+  float sum_lo = 0.0f, sum_hi = 0.0f;  // virtual threads tid and tid + 128
+  if (sm_thread) {
     for (int i = tid; i < size; i += kSoftmaxThreads) {
       const float e = expf(score_head[i] - max_val);
       score_head[i] = e;
-      sum += e;
+      sum_lo += e;
     }
-  sum = warp_tree_sum(sum);
-  if (lane == 0 && sm_thread) s_warp[warp] = sum;
+    for (int i = tid + kHalf; i < size; i += kSoftmaxThreads) {
+      const float e = expf(score_head[i] - max_val);
+      score_head[i] = e;
+      sum_hi += e;
+    }
+  }
+  sum_lo = warp_tree_sum(sum_lo);
+  sum_hi = warp_tree_sum(sum_hi);
+  if (lane == 0 && sm_thread) {
+    s_warp[warp] = sum_lo;      // virtual warp `warp`
+    s_warp[warp + 4] = sum_hi;  // virtual warp `warp + 4`
+  }
   consumer_sync<CT>();
   if (tid == 0) {
     float total = s_warp[0];
 #pragma unroll
-    for (int w = 1; w < kSmWarps; ++w) total = __fadd_rn(total, s_warp[w]);
+    for (int w = 1; w < kSoftmaxThreads / 32; ++w) total = __fadd_rn(total, s_warp[w]);
     *s_bcast = total;
   }
   consumer_sync<CT>();
-  sum = *s_bcast;
+  const float sum = *s_bcast;
   for (int i = tid; i < size; i += CT) score_head[i] = score_head[i] / sum;
   consumer_sync<CT>();
 
@@ -679,9 +678,8 @@ __device__ __noinline__ Pipe attention_phase(int head, int pos, Pipe pipe, unsig
 // With W == 1 and FOLD the rmsnorm sum of squares is accumulated in the same pass by the
 // kNormThreads threads that own the reference's chains (rmsnorm_kernel.cu:19-32).
 template <int W, int UP, bool FOLD>
-__device__ __forceinline__ float stage_exchange(const Params& P, unsigned tag, int n4, int t, int NT,
-                                                float4* xs4, float4* xres4) {
-  const unsigned long long* area = P.tp_data[P.tp_rank] + static_cast<size_t>(tag & 1u) * W * P.tp_stride;
+__device__ KLLM_STAGE_CALL float stage_exchange(const unsigned long long* area, int tp_stride, unsigned tag, int n4,
+                                                int t, int NT, float4* xs4, float4* xres4) {
   float ssq = 0.f;
   const long long t_start = clock64();
   for (int pb = t; pb < n4; pb += NT * UP) {
@@ -696,7 +694,7 @@ __device__ __forceinline__ float stage_exchange(const Params& P, unsigned tag, i
         if (p < n4) {
 #pragma unroll
           for (int r = 0; r < W; ++r) {
-            const unsigned long long* row = area + static_cast<size_t>(r) * P.tp_stride + 4 * p;
+            const unsigned long long* row = area + static_cast<size_t>(r) * tp_stride + 4 * p;
             if (W == 1) {
               ld_tagged2_gpu(row, wd[k][r][0], wd[k][r][1]);
               ld_tagged2_gpu(row + 2, wd[k][r][2], wd[k][r][3]);
@@ -754,7 +752,7 @@ __device__ __forceinline__ float stage_exchange(const Params& P, unsigned tag, i
 
 // Local hand-off (tag_in): the previous phase's output vector, polled in place.
 template <int UP>
-__device__ __forceinline__ void stage_handoff(const unsigned long long* src, unsigned tag, int n4, int t, int NT,
+__device__ KLLM_STAGE_CALL void stage_handoff(const unsigned long long* src, unsigned tag, int n4, int t, int NT,
                                               float4* xs4) {
   const long long t_start = clock64();
   for (int pb = t; pb < n4; pb += NT * UP) {
@@ -795,18 +793,16 @@ __device__ __forceinline__ void stage_handoff(const unsigned long long* src, uns
 // shared memory, RMS-normalises it when the phase asks for it, consumes this CTA's ring stages
 // task by task, runs the epilogues and, for the classifier, leaves the CTA's (max, index).
 template <int CW, bool INT8, bool PROF>
-__device__ __noinline__ Carry gemv_phase(Carry carry, int tok, int pos, const float* emb_row,
-                                         unsigned long long* stamp) {
+__device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int tok, int pos, const float* emb_row,
+                                            unsigned long long* stamp) {
   constexpr int CT = CW * 32;
   constexpr int wbytes = INT8 ? 1 : 4;
-  Ctl& c = ctl();
-  const Params& P = c.P;
-  const Phase& ph = c.ph_cons;
-  uint64_t* full_bar = c.full_bar;
-  uint64_t* empty_bar = c.empty_bar;
-  float* s_warp = c.s_warp;
-  float* s_argv = c.s_argv;
-  int* s_argi = c.s_argi;
+  const Phase& ph = g_ph_cons;
+  uint64_t* full_bar = g_full_bar;
+  uint64_t* empty_bar = g_empty_bar;
+  float* s_warp = g_s_warp;
+  float* s_argv = g_s_argv;
+  int* s_argi = g_s_argi;
   float* xs = reinterpret_cast<float*>(smem + kCtlBytes);                  // phase input vector
   float* xres = reinterpret_cast<float*>(smem + kCtlBytes + P.xbuf_bytes);  // residual stream (tagged modes)
   unsigned char* stages = smem + kCtlBytes + P.xbuf_bytes + P.xres_bytes;
@@ -830,35 +826,26 @@ __device__ __noinline__ Carry gemv_phase(Carry carry, int tok, int pos, const fl
   const int M = ph.in_dim;
   const int n4 = M >> 2;
   const bool has_norm = ph.norm_w != nullptr;
-  // up to kMaxNormRegs float4 of the (static) norm weight ride in registers while x arrives
-  constexpr int kMaxNormRegs = (4 * 256) / CT;
-  float4 nw[kMaxNormRegs];
-  const bool norm_regs = has_norm && n4 <= kMaxNormRegs * CT;
-  if (norm_regs) {
-    const float4* nw4 = reinterpret_cast<const float4*>(ph.norm_w);
-#pragma unroll
-    for (int k = 0; k < kMaxNormRegs; ++k) {
-      const int i = tid + k * CT;
-      if (i < n4) nw[k] = __ldg(nw4 + i);
-    }
-  }
   float ssq = 0.f;
   bool ssq_ready = false;
   if (ph.tp_in) {
     // x = x_old + (p_0 + ... + p_{W-1}); no grid barrier, no all-reduce kernel
     const unsigned tag = P.tp_seq_base + static_cast<unsigned>(tok * P.exch_per_token + ph.exch) + 1u;
+    const unsigned long long* area =
+        P.tp_data[P.tp_rank] + static_cast<size_t>(tag & 1u) * P.tp_world * P.tp_stride;
     switch (P.tp_world) {
       case 1:
         if (has_norm) {
-          if (tid < kNormThreads) ssq = stage_exchange<1, 4, true>(P, tag, n4, tid, kNormThreads, xs4w, xres4);
+          if (tid < kNormThreads)
+            ssq = stage_exchange<1, 4, true>(area, P.tp_stride, tag, n4, tid, kNormThreads, xs4w, xres4);
           ssq_ready = true;
         } else {
-          stage_exchange<1, 4, false>(P, tag, n4, tid, CT, xs4w, xres4);
+          stage_exchange<1, 4, false>(area, P.tp_stride, tag, n4, tid, CT, xs4w, xres4);
         }
         break;
-      case 2: stage_exchange<2, 2, false>(P, tag, n4, tid, CT, xs4w, xres4); break;
-      case 4: stage_exchange<4, 1, false>(P, tag, n4, tid, CT, xs4w, xres4); break;
-      default: stage_exchange<8, 1, false>(P, tag, n4, tid, CT, xs4w, xres4); break;
+      case 2: stage_exchange<2, 2, false>(area, P.tp_stride, tag, n4, tid, CT, xs4w, xres4); break;
+      case 4: stage_exchange<4, 1, false>(area, P.tp_stride, tag, n4, tid, CT, xs4w, xres4); break;
+      default: stage_exchange<8, 1, false>(area, P.tp_stride, tag, n4, tid, CT, xs4w, xres4); break;
     }
   } else if (ph.tag_in != nullptr) {
     stage_handoff<4>(ph.tag_in, hand_tag(ph.hand_in), n4, tid, CT, xs4w);
@@ -888,21 +875,20 @@ __device__ __noinline__ Carry gemv_phase(Carry carry, int tok, int pos, const fl
     consumer_sync<CT>();
     const float total = __fadd_rn(__fadd_rn(__fadd_rn(s_warp[0], s_warp[1]), s_warp[2]), s_warp[3]);
     const float sc = rsqrtf(__fadd_rn(__fdiv_rn(total, static_cast<float>(M)), ph.norm_eps));
-    if (norm_regs) {
-#pragma unroll
-      for (int k = 0; k < kMaxNormRegs; ++k) {
-        const int i = tid + k * CT;
-        if (i < n4) {
-          float4 v = xs4w[i];
-          v.x = __fmul_rn(__fmul_rn(sc, v.x), nw[k].x);
-          v.y = __fmul_rn(__fmul_rn(sc, v.y), nw[k].y);
-          v.z = __fmul_rn(__fmul_rn(sc, v.z), nw[k].z);
-          v.w = __fmul_rn(__fmul_rn(sc, v.w), nw[k].w);
-          xs4w[i] = v;
-        }
+    {
+      // the norm weight (dim floats, the same for every CTA and token) comes from L2 here, once the
+      // scale is known: keeping it in registers across the poll made ptxas spill, and with the ring
+      // taking all of shared memory a spill is an L2 round trip too
+      const float4* nw4 = reinterpret_cast<const float4*>(ph.norm_w);
+      for (int i = tid; i < n4; i += CT) {
+        const float4 nw = __ldg(nw4 + i);
+        float4 v = xs4w[i];
+        v.x = __fmul_rn(__fmul_rn(sc, v.x), nw.x);
+        v.y = __fmul_rn(__fmul_rn(sc, v.y), nw.y);
+        v.z = __fmul_rn(__fmul_rn(sc, v.z), nw.z);
+        v.w = __fmul_rn(__fmul_rn(sc, v.w), nw.w);
+        xs4w[i] = v;
       }
-    } else {
-      for (int i = tid; i < M; i += CT) xs[i] = __fmul_rn(__fmul_rn(sc, xs[i]), ph.norm_w[i]);
     }
   }
   consumer_sync<CT>();
@@ -1098,13 +1084,12 @@ __device__ __noinline__ Carry gemv_phase(Carry carry, int tok, int pos, const fl
 template <int CW, bool INT8, bool PROF>
 __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Params P) {
   constexpr int CT = CW * 32;  // consumer threads
-  Ctl& c = ctl();
-  uint64_t* full_bar = c.full_bar;
-  uint64_t* empty_bar = c.empty_bar;
-  Phase& s_phase_cons = c.ph_cons;
-  Phase& s_phase_prod = c.ph_prod;
-  Phase& s_phase_pf = c.ph_pf;
-  volatile unsigned& s_fill_count = c.fill_count;
+  uint64_t* full_bar = g_full_bar;
+  uint64_t* empty_bar = g_empty_bar;
+  Phase& s_phase_cons = g_ph_cons;
+  Phase& s_phase_prod = g_ph_prod;
+  Phase& s_phase_pf = g_ph_pf;
+  volatile unsigned& s_fill_count = g_fill_count;
 
   float* xres = reinterpret_cast<float*>(smem + kCtlBytes + P.xbuf_bytes);  // residual stream (tagged modes)
   unsigned char* stages = smem + kCtlBytes + P.xbuf_bytes + P.xres_bytes;
@@ -1116,11 +1101,6 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
   const int cta = blockIdx.x;
   const int G = gridDim.x;
 
-  {  // the phase functions read the kernel parameters from shared memory
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&P);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&c.P);
-    for (int i = tid; i < static_cast<int>(sizeof(Params) / 4); i += CT + 64) dst[i] = src[i];
-  }
   if (tid == 0) {
     s_fill_count = 0u;
     for (int s = 0; s < S; ++s) {
@@ -1141,7 +1121,8 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
     unsigned filled = 0u;
     int ppos = P.state->pos;
     for (int tok = 0; tok < P.n_tokens; ++tok, ++ppos) {
-      for (int pi = 0; pi < P.n_phases; ++pi) {
+      const int n_run = tok < P.skip_cls_tokens ? P.n_phases - 1 : P.n_phases;  // prompt token: no classifier
+      for (int pi = 0; pi < n_run; ++pi) {
         {
           const uint32_t* src = reinterpret_cast<const uint32_t*>(P.phases + pi);
           uint32_t* dst = reinterpret_cast<uint32_t*>(&s_phase_prod);
@@ -1264,7 +1245,8 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
     unsigned ahead = 0u;  // stages walked by this warp (same counting as the producer's `filled`)
     int ppos = P.state->pos;
     for (int tok = 0; tok < P.n_tokens; ++tok, ++ppos) {
-      for (int pi = 0; pi < P.n_phases; ++pi) {
+      const int n_run = tok < P.skip_cls_tokens ? P.n_phases - 1 : P.n_phases;
+      for (int pi = 0; pi < n_run; ++pi) {
         {
           const uint32_t* src = reinterpret_cast<const uint32_t*>(P.phases + pi);
           uint32_t* dst = reinterpret_cast<uint32_t*>(&s_phase_pf);
@@ -1364,7 +1346,7 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
       if (stamp) stamp[0] = global_ns();
 
       if (ph.kind == kPhaseAttention) {
-        if (cta < P.head_num) pipe = attention_phase<CW>(cta, pos, pipe, hand_tag(ph.hand_in), hand_tag(ph.hand_out));
+        if (cta < P.head_num) pipe = attention_phase<CW>(P, cta, pos, pipe, hand_tag(ph.hand_in), hand_tag(ph.hand_out));
         if (stamp) stamp[1] = stamp[2] = global_ns();
         if (ph.barrier_after) grid_barrier<CT>(P.barrier, bar_target, G);
         prev_barrier = ph.barrier_after != 0;
@@ -1373,8 +1355,11 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
       }
       prev_barrier = ph.barrier_after != 0;
 
-      {
-        const Carry out = gemv_phase<CW, INT8, PROF>(Carry{pipe, best.v, best.i}, tok, pos, emb_row, stamp);
+      // A prompt token (llama3.cpp:733-745: predict(..., is_prompt = true) discards the logits and
+      // returns -1) skips the classifier -- its weights are not even streamed -- but keeps the grid
+      // barrier that closes the token.
+      if (!(ph.argmax && tok < P.skip_cls_tokens)) {
+        const Carry out = gemv_phase<CW, INT8, PROF>(P, Carry{pipe, best.v, best.i}, tok, pos, emb_row, stamp);
         pipe = out.pipe;
         best.v = out.best_v, best.i = out.best_i;
       }
@@ -1419,9 +1404,12 @@ namespace {
 // PROF: the instantiation kllm_decoder_profile launches (its stamps cost registers in the row loops)
 template <bool PROF>
 const void* kernel_for(int consumer_warps, bool int8) {
-  if (int8)
-    return consumer_warps == 16 ? reinterpret_cast<const void*>(mega::decode_megakernel<16, true, PROF>)
-                                : reinterpret_cast<const void*>(mega::decode_megakernel<8, true, PROF>);
+  if (int8) {
+    if (consumer_warps == 16) return reinterpret_cast<const void*>(mega::decode_megakernel<16, true, PROF>);
+    if (consumer_warps == 6) return reinterpret_cast<const void*>(mega::decode_megakernel<6, true, PROF>);
+    return reinterpret_cast<const void*>(mega::decode_megakernel<8, true, PROF>);
+  }
+  if (consumer_warps == 6) return reinterpret_cast<const void*>(mega::decode_megakernel<6, false, PROF>);
   return reinterpret_cast<const void*>(mega::decode_megakernel<8, false, PROF>);
 }
 }  // namespace
@@ -1458,9 +1446,12 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   }
   // consumer warps: int8 rows are bound by instruction issue (4 instructions per weight byte), so
   // they get 16 warps of <= 112 registers; fp32 rows by shared-memory bandwidth, 8 fat warps
-  consumer_warps_ = int8 ? 16 : 8;
-  if (const char* e = getenv("KLLM_CONSUMER_WARPS"))
-    if (int8 && (atoi(e) == 8 || atoi(e) == 16)) consumer_warps_ = atoi(e);
+  consumer_warps_ = int8 ? 16 : 6;
+  if (const char* e = getenv("KLLM_CONSUMER_WARPS")) {
+    const int v = atoi(e);
+    if (int8 && (v == 6 || v == 8 || v == 16)) consumer_warps_ = v;
+    if (!int8 && (v == 6 || v == 8)) consumer_warps_ = v;
+  }
   kernel_ = kernel_for<false>(consumer_warps_, int8);
   kernel_prof_ = kernel_for<true>(consumer_warps_, int8);
   threads_ = consumer_warps_ * 32 + 64;
@@ -1485,7 +1476,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   xbuf = std::max(xbuf, attn_ws);
   xbuf = (xbuf + 127) & ~127;
   const int xres = tagged_ ? ((dim * 4 + 127) & ~127) : 0;  // the CTA's copy of the residual stream
-  const int budget = max_smem - mega::kCtlBytes - xbuf - xres - 256;  // control block + slack
+  const int budget = max_smem - xbuf - xres - 2048;  // static shared memory + slack
   // Stage size: whole rows, so pick it to waste little of the ring on the model's row lengths.
   // fp32: 32 KB (4 rows of dim 2048, 2 of 4096).  int8: 27 KB = 6 rows of dim 4096 (+ scales) or
   // 2 rows of hidden 11008, which leaves six stages next to the 44 KB input vector and the 16 KB
@@ -1499,7 +1490,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   if (stages < 2) return KLLM_E_UNSUPPORTED;
   stage_bytes_ = stage_bytes;
   stages_ = stages;
-  attn_tile_ = std::min(stage_bytes / (hs * 4), mega::kSoftmaxThreads) & ~31;
+  attn_tile_ = std::min(stage_bytes / (hs * 4), consumer_warps_ * 32) & ~31;  // one timestep per consumer thread
   if (attn_tile_ < 32) return KLLM_E_UNSUPPORTED;
   xbuf_bytes_ = xbuf;
   xres_bytes_ = xres;
@@ -1752,13 +1743,14 @@ void MegaEngine::destroy() {
 }
 
 int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long* prof_dev,
-                    int prof_token) {
+                    int prof_token, int skip_cls_tokens) {
   if (!ready_) return KLLM_E_STATE;
   Params P{};
   const MegaModel& m = model_;
   P.phases = static_cast<const Phase*>(d_phases_);
   P.n_phases = n_phases_;
   P.n_tokens = n_tokens;
+  P.skip_cls_tokens = skip_cls_tokens;
   P.num_stages = stages_;
   P.stage_bytes = stage_bytes_;
   P.xbuf_bytes = xbuf_bytes_;

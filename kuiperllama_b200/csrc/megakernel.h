@@ -77,6 +77,7 @@ struct State {  // == StepState in decoder.cu
 struct Params {
   const Phase* phases;
   int n_phases, n_tokens;
+  int skip_cls_tokens;  // the first skip_cls_tokens positions of this launch are prompt tokens: no classifier pass
   int num_stages, stage_bytes, xbuf_bytes;
   int xres_bytes;  // shared-memory copy of the residual stream behind the input vector (tagged modes; else 0)
   int attn_tile;  // timesteps per K/V ring stage
@@ -152,7 +153,7 @@ class MegaEngine {
   void destroy();
   // Run n_tokens consecutive positions starting from the device-resident state.
   int run(int n_tokens, const int32_t* teacher_dev, unsigned long long* prof_dev = nullptr,
-          int prof_token = -1);
+          int prof_token = -1, int skip_cls_tokens = 0);
   int grid() const { return grid_; }
   bool ready() const { return ready_; }
   int stages() const { return stages_; }

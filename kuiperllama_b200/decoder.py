@@ -219,6 +219,24 @@ class Decoder:
               "kllm_decoder_step")
         return nxt.value
 
+    def prompt(self, tokens, start_pos: int = 0) -> int:
+        """Feed a whole prompt (one launch on the persistent engine, classifier only for the last
+        position); returns the greedy id that follows the prompt."""
+        n = len(tokens)
+        arr = (ctypes.c_int32 * n)(*[int(t) for t in tokens])
+        nxt = ctypes.c_int32(-1)
+        check(self.lib.kllm_decoder_prompt(self.handle, arr, n, start_pos, ctypes.byref(nxt)), "kllm_decoder_prompt")
+        return nxt.value
+
+    def prefill_tf32(self, tokens, start_pos: int = 0) -> int:
+        """TOLERANCED batched prefill on the tcgen05 tensor cores (TF32); same contract as prompt()."""
+        n = len(tokens)
+        arr = (ctypes.c_int32 * n)(*[int(t) for t in tokens])
+        nxt = ctypes.c_int32(-1)
+        check(self.lib.kllm_decoder_prefill_tf32(self.handle, arr, n, start_pos, ctypes.byref(nxt)),
+              "kllm_decoder_prefill_tf32")
+        return nxt.value
+
     def generate(self, first_token: int, start_pos: int, n_steps: int, teacher=None):
         out = (ctypes.c_int32 * n_steps)()
         tf = None

@@ -354,3 +354,32 @@ def test_qwen25_05b_full_size(kllm_lib, oracle, engine):
     else:
         case["free"] = (engine, ids, lg)
     dec.close()
+
+
+@pytest.mark.parametrize("key", ["small", "small-int8", "small-qwen"])
+def test_prompt_call_equals_stepping(kllm_lib, key):
+    """kllm_decoder_prompt (one launch, classifier skipped for all but the last prompt position --
+    llama3.cpp:738-739 throws those logits away) leaves the same KV cache, logits and next id as
+    predict()-style stepping with is_prompt = true, bit for bit, and decoding continues identically."""
+    from kuiperllama_b200 import SHAPES, synth_weights
+    shape = SHAPES[key]
+    w = synth_weights(shape, "cuda", 21)
+    rng = np.random.default_rng(5)
+    toks = [1] + [int(t) for t in rng.integers(2, shape.vocab_size, 37)]
+    a = make_decoder(shape, w)
+    nxt_a = a.prompt(toks)
+    ka, va = a.kv_cache()
+    la = a.logits()
+    b = make_decoder(shape, w)
+    nb = -2
+    for pos, t in enumerate(toks):
+        nb = b.step(t, pos, is_prompt=(pos < len(toks) - 1))
+        assert (nb == -1) == (pos < len(toks) - 1)
+    kb, vb = b.kv_cache()
+    n = len(toks)
+    assert nxt_a == nb
+    assert_bit_equal(ka[:, :n], kb[:, :n], "key cache after the prompt")
+    assert_bit_equal(va[:, :n], vb[:, :n], "value cache after the prompt")
+    assert_bit_equal(la, b.logits(), "logits of the last prompt position")
+    assert a.generate(nxt_a, n, 24) == b.generate(nb, n, 24)
+    a.close(); b.close()
