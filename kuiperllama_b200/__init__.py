@@ -114,6 +114,9 @@ def load_library(path: str | Path | None = None) -> ctypes.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
+    import os
+    if path is None and os.environ.get("KLLM_LIB"):  # experiments: a variant build of the same C-ABI
+        path = os.environ["KLLM_LIB"]
     p = Path(path) if path else LIB_PATH
     if not p.exists():
         raise KllmError(
@@ -127,7 +130,7 @@ def load_library(path: str | Path | None = None) -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError = missing export: fail loudly
         fn.restype = restype
         fn.argtypes = argtypes
-    if path is None:
+    if path is None or os.environ.get("KLLM_LIB") == str(path):
         _lib = lib
     return lib
 

@@ -43,6 +43,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "../../include/kllm_b200.h"
@@ -55,6 +56,12 @@ namespace mega {
 
 // The phase bodies are written as functions but inlined: real calls make ptxas spill around them,
 // and with the ring taking all of shared memory there is no L1 left -- a spill is an L2 round trip.
+#ifndef KLLM_MBAR_HINT_NS
+#define KLLM_MBAR_HINT_NS 20000u
+#endif
+#ifndef KLLM_TASK_ROWS
+#define KLLM_TASK_ROWS 4
+#endif
 #ifndef KLLM_PHASE_CALL
 #define KLLM_PHASE_CALL __forceinline__
 #endif
@@ -82,12 +89,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
 }
+// try_wait suspends the warp in hardware until the phase completes or the time hint (ns) runs out:
+// with a generous hint a waiting warp sleeps instead of re-issuing the probe -- waiting warps
+// otherwise compete for issue slots with the warps that are computing on the same scheduler
+// (ncu, r02f: SYNCS + BRA + YIELD of the spin loops were a quarter of all executed instructions).
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   asm volatile(
       "{\n .reg .pred p;\n WAIT_%=:\n"
-      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       " @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}" ::"r"(smem_u32(b)),
-      "r"(parity)
+      "r"(parity), "r"(KLLM_MBAR_HINT_NS)
       : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
@@ -431,6 +442,129 @@ __device__ __forceinline__ void accum_w8_any(const uint32_t (&w)[NR], const uint
   if ((full_chunks << 7) + (lane << 2) < M) one(full_chunks);
 }
 
+// ---- int8 weights x fixed-point activations on the integer dot-product unit (TOLERANCED) ---------
+// The exact int8 loop above is bound by instruction issue: four instructions per weight byte
+// (PRMT + FADD to convert, FMUL by the group scale, FFMA), ~21 warp instructions per 128 weight
+// bytes against ~5.6 bytes per clock per scheduler that HBM can deliver.  The fast mode turns the
+// activations of each 64-element group into 24-bit fixed point once per phase --
+//     x_i ~= step_g * q_i,  q_i = round(x_i / step_g),  step_g = max|x in group| / 2^22,
+// q_i split into three balanced base-256 digits l2 l1 l0 (int8 each) -- and then needs ONE dp4a per
+// 4 weights and digit: sum_i w_i x_i = s_g * step_g * (65536 D2 + 256 D1 + D0), D_k = sum_i w_i l_k,i
+// exact in int32.  ~6 warp instructions per 128 weight bytes.  The group scale s_g and the int8
+// weights enter exactly as in the reference (dequantised weight = q * s, export.py:60-67); only x is
+// rounded, to 2^-23 of its group maximum -- the same order as fp32 rounding of the products
+// themselves.  Logits agree with the exact mode to ~1e-6 relative (tests: <= 1e-4 absolute, same
+// greedy id wherever the top-2 margin exceeds 2e-4), not bit for bit.
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int dp4a4(const uint4& w, const uint4& l) {
+  int d = __dp4a(static_cast<int>(w.x), static_cast<int>(l.x), 0);
+  d = __dp4a(static_cast<int>(w.y), static_cast<int>(l.y), d);
+  d = __dp4a(static_cast<int>(w.z), static_cast<int>(l.z), d);
+  return __dp4a(static_cast<int>(w.w), static_cast<int>(l.w), d);
+}
+// exact int32 -> fp32 for |d| < 2^22 without the slow conversion pipe: 1.5 * 2^23 + d is exact
+__device__ __forceinline__ float small_int_to_float(int d) {
+  return __fsub_rn(__int_as_float(0x4B400000 + d), 12582912.0f);
+}
+// In-place layout (fast mode): the 256 bytes that held the fp32 values of 64-element group g hold four
+// 64-byte regions -- the three digit planes of the group and its step.  Digit plane k sits in region
+// (k + (g & 1)) & 3, the step in region (3 + (g & 1)) & 3: alternating the region order between even
+// and odd groups makes the 32 lanes of a 128-bit load (8 groups x 4 quarters) hit all 8 distinct
+// 16-byte bank slots, 4 lanes each -- the minimum of 4 wavefronts.  Quarter q (16 elements) of a
+// plane is the 16-byte chunk q of its region.
+template <int NR>
+__device__ __forceinline__ void accum_w8_dp4a(const uint32_t (&w)[NR], const uint32_t (&sc)[NR], uint32_t x, int M,
+                                              int lane, float (&acc)[NR]) {
+  // lane owns 16 consecutive elements per step of 512: group = 8 * step + lane / 4, quarter = lane % 4
+  const uint32_t odd = (lane >> 2) & 1u;
+  const uint32_t gq = x + (lane >> 2) * 256 + (lane & 3) * 16;
+  const uint32_t l0 = gq + ((0u + odd) & 3u) * 64, l1 = gq + ((1u + odd) & 3u) * 64, l2 = gq + ((2u + odd) & 3u) * 64;
+  const uint32_t xsp = x + (lane >> 2) * 256 + ((3u + odd) & 3u) * 64;
+  uint32_t wp[NR], sp[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) {
+    wp[r] = w[r] + lane * 16;
+    sp[r] = sc[r] + (lane >> 2) * 4;
+  }
+  const int steps = (M + 511) >> 9;
+#pragma unroll 2
+  for (int it = 0; it < steps; ++it) {
+    if (it * 512 + lane * 16 < M) {  // M % 512 != 0: the last step covers part of the lanes (M % 64 == 0)
+      const uint4 a0 = lds_u4(l0 + it * 2048), a1 = lds_u4(l1 + it * 2048), a2 = lds_u4(l2 + it * 2048);
+      const float xstep = lds_f32(xsp + it * 2048);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        const uint4 wv = lds_u4(wp[r] + it * 512);
+        const float ws = lds_f32(sp[r] + it * 32);
+        const float c0 = small_int_to_float(dp4a4(wv, a0));
+        const float c1 = small_int_to_float(dp4a4(wv, a1));
+        const float c2 = small_int_to_float(dp4a4(wv, a2));
+        const float f = __fmaf_rn(c2, 65536.0f, __fmaf_rn(c1, 256.0f, c0));
+        acc[r] = __fmaf_rn(f, __fmul_rn(xstep, ws), acc[r]);
+      }
+    }
+  }
+}
+
+// The phase's input vector (fp32, M floats at xs, M % 64 == 0) -> digit planes + step per group, in
+// place (layout above).  Four adjacent lanes share a group: each reads its 16 values, the group
+// maximum is folded with two shuffles, and after a warp-level sync (all four have read) each lane
+// overwrites its quarter -- no CTA barrier, no values parked in registers.
+template <int CT>
+__device__ __noinline__ void quantize_input_inplace(float* xs, int M, int tid) {
+  const int quarters = M >> 4;
+  for (int base = 0; base < quarters; base += CT) {  // CT % 32 == 0: whole warps, groups never straddle one
+    const int qg = base + tid;
+    const bool on = qg < quarters;
+    float4 v[4];
+    float gmax = 0.f;
+    if (on) {
+      const float4* g4 = reinterpret_cast<const float4*>(xs) + qg * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = g4[j];
+        gmax = fmaxf(gmax, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
+      }
+    }
+    gmax = fmaxf(gmax, __shfl_xor_sync(kFull, gmax, 1));
+    gmax = fmaxf(gmax, __shfl_xor_sync(kFull, gmax, 2));  // also orders: every lane of the group has read
+    const float step = gmax * (1.0f / 4194304.0f);      // 2^-22
+    const float inv = gmax > 0.f ? 4194304.0f / gmax : 0.f;
+    __syncwarp();
+    if (on) {
+      const int g = qg >> 2, q = qg & 3;
+      const unsigned odd = g & 1;
+      unsigned char* gb = reinterpret_cast<unsigned char*>(xs) + g * 256 + q * 16;
+      uint32_t* o0 = reinterpret_cast<uint32_t*>(gb + ((0u + odd) & 3u) * 64);
+      uint32_t* o1 = reinterpret_cast<uint32_t*>(gb + ((1u + odd) & 3u) * 64);
+      uint32_t* o2 = reinterpret_cast<uint32_t*>(gb + ((2u + odd) & 3u) * 64);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {  // 4 elements -> one word of each digit plane, written at once
+        const float e[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+        uint32_t p0 = 0, p1 = 0, p2 = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int qv = __float2int_rn(e[b] * inv);  // |qv| <= 2^22
+          const int a0 = ((qv + 128) & 255) - 128;    // balanced digits: qv = 65536 a2 + 256 a1 + a0
+          const int q1 = (qv - a0) >> 8;
+          const int a1 = ((q1 + 128) & 255) - 128;
+          const int a2 = (q1 - a1) >> 8;
+          p0 |= static_cast<uint32_t>(a0 & 255) << (8 * b);
+          p1 |= static_cast<uint32_t>(a1 & 255) << (8 * b);
+          p2 |= static_cast<uint32_t>(a2 & 255) << (8 * b);
+        }
+        o0[j] = p0, o1[j] = p1, o2[j] = p2;
+      }
+      if (q == 0) *reinterpret_cast<float*>(gb + ((3u + odd) & 3u) * 64) = step;
+    }
+  }
+  consumer_sync<CT>();
+}
+
 // Dot products of the NR rows of a task (shared-window addresses of the rows and of their int8
 // scales); every lane gets every total.  Deliberately NOT inlined: as part of the megakernel's one
 // big function the row loops inherit its register pressure and ptxas then serialises every
@@ -441,7 +575,7 @@ struct Rows4 {
 };
 template <int NR, bool INT8>
 __device__ __forceinline__ float4 dot_rows(Rows4 rows, Rows4 scales, uint32_t x, int M, int group_size,
-                                        int group_shift, int lane) {
+                                           int group_shift, int lane, bool fast = false) {
   float acc[NR][4];
 #pragma unroll
   for (int r = 0; r < NR; ++r)
@@ -455,6 +589,20 @@ __device__ __forceinline__ float4 dot_rows(Rows4 rows, Rows4 scales, uint32_t x,
     sc[r] = scales.a[r];
   }
   if constexpr (INT8) {
+    if (fast) {  // fixed-point activations x int8 weights on dp4a (toleranced mode; group size 64)
+      float a1[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) a1[r] = 0.f;
+      accum_w8_dp4a<NR>(w, sc, x, M, lane, a1);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        float v = a1[r];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+        d[r] = v;
+      }
+      return make_float4(d[0], d[1], d[2], d[3]);
+    }
     if (group_size == 64)
       accum_w8_g64<NR>(w, sc, x, M, lane, acc);
     else
@@ -835,7 +983,13 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
         P.tp_data[P.tp_rank] + static_cast<size_t>(tag & 1u) * P.tp_world * P.tp_stride;
     switch (P.tp_world) {
       case 1:
-        if (has_norm) {
+        // Many thin warps (int8 build, 96 registers): all threads poll two packs each -- the poll
+        // buffers of a deeper batch would spill, and a spill is an L2 round trip here; the sum of
+        // squares is then taken from shared memory.  Few fat warps: the 128 rmsnorm threads poll four
+        // packs each and fold the sum of squares into the same pass.
+        if (CW >= 16) {
+          stage_exchange<1, 2, false>(area, P.tp_stride, tag, n4, tid, CT, xs4w, xres4);
+        } else if (has_norm) {
           if (tid < kNormThreads)
             ssq = stage_exchange<1, 4, true>(area, P.tp_stride, tag, n4, tid, kNormThreads, xs4w, xres4);
           ssq_ready = true;
@@ -848,7 +1002,10 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
       default: stage_exchange<8, 1, false>(area, P.tp_stride, tag, n4, tid, CT, xs4w, xres4); break;
     }
   } else if (ph.tag_in != nullptr) {
-    stage_handoff<4>(ph.tag_in, hand_tag(ph.hand_in), n4, tid, CT, xs4w);
+    if (CW >= 16)
+      stage_handoff<2>(ph.tag_in, hand_tag(ph.hand_in), n4, tid, CT, xs4w);
+    else
+      stage_handoff<4>(ph.tag_in, hand_tag(ph.hand_in), n4, tid, CT, xs4w);
   } else {
     const float4* xg4 = reinterpret_cast<const float4*>(ph.x_from_emb ? emb_row : ph.x);
     for (int i = tid; i < n4; i += CT) xs4w[i] = __ldcg(xg4 + i);
@@ -892,6 +1049,11 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
     }
   }
   consumer_sync<CT>();
+  // int8 fast mode: the staged (and normalised) vector becomes 24-bit fixed point per 64-group
+  const bool int8_fast = INT8 && P.int8_fast != 0 && ph.group_size == 64 && (M & 63) == 0;
+  if constexpr (INT8) {
+    if (int8_fast) quantize_input_inplace<CT>(xs, M, tid);
+  }
   if (stamp) stamp[1] = global_ns();
 
   const int u0 = static_cast<int>(static_cast<long long>(cta) * ph.units / G);
@@ -951,7 +1113,11 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
     // A stage holds n units; they are handed out as tasks of up to 4 rows (plain: 4 units, SwiGLU:
     // 2 units = w1 + w3 rows of two outputs), task after task round-robin over the consumer warps.
     const int ups = ph.rows_per_stage / rpu;
-    const int upt = ph.swiglu ? 2 : 4;  // units per task
+    // Rows per task (compile-time knob KLLM_TASK_ROWS: 1, 2 or 4).  A CTA owns only 14-83 rows of a
+    // phase and every consumer warp has to pass (wait + arrive) every ring stage in order, so a warp
+    // sitting on a fat task while its neighbours have none holds up the refill of the whole ring.
+    constexpr int kTaskRows = KLLM_TASK_ROWS;
+    const int upt = ph.swiglu ? (kTaskRows >= 2 ? kTaskRows / 2 : 1) : kTaskRows;  // units per task
     int task = 0;                      // tasks of this phase so far (same count in every warp)
     for (int u = u0; u < u1; u += ups) {
       const int n = min(ups, u1 - u);
@@ -974,36 +1140,36 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
         const uint32_t xa = smem_u32(xs);
         if (ph.swiglu) {
           // stage order: w1 rows of the n units, then their w3 rows
-          if (nu == 2) {
+          if (kTaskRows == 4 && nu == 2) {
             const Rows4 rp{{wa + i0 * rb, wa + (n + i0) * rb, wa + (i0 + 1) * rb, wa + (n + i0 + 1) * rb}};
             const Rows4 sp{{sa + i0 * srb, sa + (n + i0) * srb, sa + (i0 + 1) * srb, sa + (n + i0 + 1) * srb}};
-            const float4 d = dot_rows<4, INT8>(rp, sp, xa, M, ph.group_size, ph.group_shift, lane);
+            const float4 d = dot_rows<4, INT8>(rp, sp, xa, M, ph.group_size, ph.group_shift, lane, int8_fast);
             e0 = lane == 0 ? d.x : d.z;
             e1 = lane == 0 ? d.y : d.w;
           } else {
             const Rows4 rp{{wa + i0 * rb, wa + (n + i0) * rb, 0u, 0u}};
             const Rows4 sp{{sa + i0 * srb, sa + (n + i0) * srb, 0u, 0u}};
-            const float4 d = dot_rows<2, INT8>(rp, sp, xa, M, ph.group_size, ph.group_shift, lane);
+            const float4 d = dot_rows<2, INT8>(rp, sp, xa, M, ph.group_size, ph.group_shift, lane, int8_fast);
             e0 = d.x, e1 = d.y;
           }
-        } else if (nu == 4) {
+        } else if (kTaskRows == 4 && nu == 4) {
           const Rows4 rp{{wa + i0 * rb, wa + (i0 + 1) * rb, wa + (i0 + 2) * rb, wa + (i0 + 3) * rb}};
           const Rows4 sp{{sa + i0 * srb, sa + (i0 + 1) * srb, sa + (i0 + 2) * srb, sa + (i0 + 3) * srb}};
-          const float4 d = dot_rows<4, INT8>(rp, sp, xa, M, ph.group_size, ph.group_shift, lane);
+          const float4 d = dot_rows<4, INT8>(rp, sp, xa, M, ph.group_size, ph.group_shift, lane, int8_fast);
           e0 = lane == 0 ? d.x : lane == 1 ? d.y : lane == 2 ? d.z : d.w;
         } else {
           int r0 = 0;
           if (nu >= 2) {
             const Rows4 rp{{wa + i0 * rb, wa + (i0 + 1) * rb, 0u, 0u}};
             const Rows4 sp{{sa + i0 * srb, sa + (i0 + 1) * srb, 0u, 0u}};
-            const float4 d = dot_rows<2, INT8>(rp, sp, xa, M, ph.group_size, ph.group_shift, lane);
+            const float4 d = dot_rows<2, INT8>(rp, sp, xa, M, ph.group_size, ph.group_shift, lane, int8_fast);
             e0 = lane == 0 ? d.x : d.y;
             r0 = 2;
           }
           if (r0 < nu) {  // nu is 1 or 3: one more row
             const Rows4 rp{{wa + (i0 + r0) * rb, 0u, 0u, 0u}};
             const Rows4 sp{{sa + (i0 + r0) * srb, 0u, 0u, 0u}};
-            const float4 d = dot_rows<1, INT8>(rp, sp, xa, M, ph.group_size, ph.group_shift, lane);
+            const float4 d = dot_rows<1, INT8>(rp, sp, xa, M, ph.group_size, ph.group_shift, lane, int8_fast);
             if (lane == r0) e0 = d.x;
           }
         }
@@ -1449,9 +1615,13 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   consumer_warps_ = int8 ? 16 : 6;
   if (const char* e = getenv("KLLM_CONSUMER_WARPS")) {
     const int v = atoi(e);
-    if (int8 && (v == 6 || v == 8 || v == 16)) consumer_warps_ = v;
+    if (int8 && (v == 6 || v == 8 || v == 16)) consumer_warps_ = v;  // fast mode: CT >= 192 quantises M <= 16384 in <= 6 rounds
     if (!int8 && (v == 6 || v == 8)) consumer_warps_ = v;
   }
+  // int8 arithmetic: "exact" reproduces the reference's fma(x * scale, float(w), acc) per element bit for
+  // bit; "fast" (KLLM_INT8_MODE=fast) is the dp4a fixed-point mode (toleranced, ~3.5x fewer instructions)
+  int8_fast_ = 0;
+  if (const char* e = getenv("KLLM_INT8_MODE")) int8_fast_ = (int8 && std::string(e) == "fast") ? 1 : 0;
   kernel_ = kernel_for<false>(consumer_warps_, int8);
   kernel_prof_ = kernel_for<true>(consumer_warps_, int8);
   threads_ = consumer_warps_ * 32 + 64;
@@ -1751,6 +1921,7 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
   P.n_phases = n_phases_;
   P.n_tokens = n_tokens;
   P.skip_cls_tokens = skip_cls_tokens;
+  P.int8_fast = int8_fast_;
   P.num_stages = stages_;
   P.stage_bytes = stage_bytes_;
   P.xbuf_bytes = xbuf_bytes_;

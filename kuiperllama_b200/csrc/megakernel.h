@@ -77,6 +77,7 @@ struct State {  // == StepState in decoder.cu
 struct Params {
   const Phase* phases;
   int n_phases, n_tokens;
+  int int8_fast;        // int8 weights: 1 = fixed-point activations on dp4a (toleranced), 0 = the reference's per-element order
   int skip_cls_tokens;  // the first skip_cls_tokens positions of this launch are prompt tokens: no classifier pass
   int num_stages, stage_bytes, xbuf_bytes;
   int xres_bytes;  // shared-memory copy of the residual stream behind the input vector (tagged modes; else 0)
@@ -161,6 +162,7 @@ class MegaEngine {
   int phases() const { return n_phases_; }
   int attn_tile() const { return attn_tile_; }
   int consumer_warps() const { return consumer_warps_; }
+  bool int8_fast() const { return int8_fast_ != 0; }
 
  private:
   MegaModel model_{};
@@ -177,6 +179,7 @@ class MegaEngine {
   unsigned tp_seq_base_ = 0, hand_base_ = 0;
   int grid_ = 0, stages_ = 0, stage_bytes_ = 0, xbuf_bytes_ = 0, xres_bytes_ = 0, n_phases_ = 0, attn_tile_ = 0;
   int consumer_warps_ = 8, threads_ = 0;
+  int int8_fast_ = 0;
   const void* kernel_ = nullptr;       // decode_megakernel<consumer warps, int8, false>
   const void* kernel_prof_ = nullptr;  // ... <.., true>: records the phase timeline stamps
   int n_barriers_per_token_ = 0;
