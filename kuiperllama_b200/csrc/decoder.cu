@@ -506,6 +506,7 @@ int kllm_decoder_prefill_tf32(kllm_decoder* dc, const int32_t* tokens_host, int3
   m.dim = d.dim, m.hidden_dim = d.hidden_dim, m.layer_num = d.layer_num, m.head_num = d.head_num;
   m.kv_head_num = d.kv_head_num, m.vocab_size = d.vocab_size, m.seq_len = d.seq_len, m.head_size = hs;
   m.flavour = d.flavour, m.mega_layout = dc->use_mega ? 1 : 0, m.eps = flavour_eps(d.flavour);
+  m.attn_split = dc->use_mega ? dc->mega.attn_split() : 1;
   m.tok_emb = d.tok_emb, m.attn_norm = dc->attn_norm.data(), m.ffn_norm = dc->ffn_norm.data();
   m.wq = dc->wq.data(), m.wk = dc->wk.data(), m.wv = dc->wv.data(), m.wo = dc->wo.data();
   m.w1 = dc->w1.data(), m.w2 = dc->w2.data(), m.w3 = dc->w3.data();
@@ -625,11 +626,12 @@ int kllm_decoder_read_kv(kllm_decoder* dc, float* key_host, float* value_host) {
     KLLM_TRY(cudaMemcpy(key_host, dc->kcache, n * sizeof(float), cudaMemcpyDeviceToHost));
     return static_cast<int>(cudaMemcpy(value_host, dc->vcache, n * sizeof(float), cudaMemcpyDeviceToHost));
   }
-  // persistent engine: K [L][kvh][hs/4][S][4], V [L][kvh][S][hs] -> reference [L][S][kv_dim]
+  // persistent engine: K [L][kvh][hs/4][S][4], V [L][kvh][SP][S][hs/SP] -> reference [L][S][kv_dim]
   std::vector<float> kraw(n), vraw(n);
   KLLM_TRY(cudaMemcpy(kraw.data(), dc->kcache, n * sizeof(float), cudaMemcpyDeviceToHost));
   KLLM_TRY(cudaMemcpy(vraw.data(), dc->vcache, n * sizeof(float), cudaMemcpyDeviceToHost));
   const size_t nh = kvd / hs;
+  const size_t SP = static_cast<size_t>(dc->mega.attn_split()), dv = hs / SP;
   for (size_t l = 0; l < L; ++l)
     for (size_t g = 0; g < nh; ++g) {
       const float* kb = kraw.data() + (l * nh + g) * S * hs;
@@ -638,7 +640,7 @@ int kllm_decoder_read_kv(kllm_decoder* dc, float* key_host, float* value_host) {
         for (size_t i = 0; i < hs; ++i) {
           const size_t dst = (l * S + t) * kvd + g * hs + i;
           key_host[dst] = kb[((i >> 2) * S + t) * 4 + (i & 3)];
-          value_host[dst] = vb[t * hs + i];
+          value_host[dst] = vb[((i / dv) * S + t) * dv + i % dv];
         }
     }
   return 0;

@@ -42,6 +42,7 @@ int comm_tagged_areas(kllm_comm* comm, unsigned long long** areas8, int* world, 
 struct PrefillModel {
   int dim, hidden_dim, layer_num, head_num, kv_head_num, vocab_size, seq_len, head_size, flavour;
   int mega_layout;  // 1: the persistent engine's head-major K / V cache layout (megakernel.cu)
+  int attn_split;   // ... whose V rows are cut into attn_split slices of head_size / attn_split dims
   float eps;
   const float* tok_emb;
   const float* const* attn_norm;

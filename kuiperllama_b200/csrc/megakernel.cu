@@ -628,48 +628,52 @@ __device__ __forceinline__ void arg_fold(ArgBest& a, float ov, int oi) {
   }
 }
 
-// ---- attention phase: one CTA per query head (mha_kernel.cu:47-110 + rope_kernel.cu) ------------
+// (defined below; the P.V phase polls its scores with it)
+template <int UP>
+__device__ KLLM_STAGE_CALL void stage_handoff(const unsigned long long* src, unsigned tag, int n4, int t, int NT,
+                                              float4* xs4);
+
+// ---- attention: SP CTAs per query head, two phases (mha_kernel.cu:47-110 + rope_kernel.cu) ---------
+// The reference gives a head one CTA and so did round 1: 32 of 148 SMs worked while the rest polled,
+// and the time grew with the context.  Every score (one left-to-right FFMA chain per timestep) and
+// every output element (one FFMA chain over the timesteps) is independent of the others, so the work
+// splits over SP CTAs per head WITHOUT touching a single chain -- results stay bit-identical:
+//   scores phase  CTA (head, s) rotates q (and the new key row), takes the K tiles j = s, s + SP, ...
+//                 and publishes its scaled scores as tagged words scores[head][t];
+//   P.V phase     CTA (head, s) polls all pos + 1 scores of the head, runs the softmax (every CTA of
+//                 the head the same bits), and owns output dims [s dv, (s + 1) dv), dv = head_size / SP:
+//                 it streams only that slice of V and publishes its dv outputs.
 // KV layout (persistent engine only; kllm_decoder_read_kv converts back):
 //   K [L][kv_head][head_size/4][seq_len][4]   -- 16-byte chunk c of timestep t at ((c*seq_len)+t)*4:
 //       a tile of T timesteps is hs/4 contiguous runs of T*16 bytes, and "thread t reads chunk c"
 //       is a conflict-free 128-bit shared-memory access (consecutive t -> consecutive 16 B);
-//   V [L][kv_head][seq_len][head_size]        -- a tile of T timesteps is one contiguous block and
-//       "thread i walks column i" is conflict-free.
+//   V [L][kv_head][SP][seq_len][dv]           -- a tile of T timesteps of one slice is one contiguous
+//       block and "thread i walks column i" is conflict-free.
 // Rows t < pos were written by earlier tokens, so -- like weights -- the producer warp streams
-// them through the ring ahead of time (K tiles first, then V tiles); only row pos is handled
-// here from registers / a direct load.
+// them through the ring ahead of time; only row pos is handled here from registers.
 __device__ __forceinline__ int attn_tiles(int pos, int T) { return (pos + T - 1) / T; }
+// tiles j = s, s + SP, ... < n
+__device__ __forceinline__ int own_tiles(int n, int s, int SP) { return n > s ? (n - s + SP - 1) / SP : 0; }
 
 template <int CW>
-__device__ KLLM_PHASE_CALL Pipe attention_phase(const Params& P, int head, int pos, Pipe pipe, unsigned tag_in,
-                                                 unsigned tag_out) {
+__device__ KLLM_PHASE_CALL Pipe attention_scores_phase(const Params& P, int head, int split, int pos, Pipe pipe,
+                                                        unsigned tag_in, unsigned tag_out) {
   const Phase& ph = g_ph_cons;
   float* ws = reinterpret_cast<float*>(smem);
-  float* s_warp = g_s_warp;
-  float* s_bcast = &g_s_bcast;
   unsigned char* stages = smem + P.xbuf_bytes + P.xres_bytes;
   uint64_t* full_bar = g_full_bar;
   uint64_t* empty_bar = g_empty_bar;
   constexpr int CT = CW * 32;
   const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const int hs = P.head_size, seq_len = P.seq_len, T = P.attn_tile, S = P.num_stages;
+  const int lane = tid & 31;
+  const int hs = P.head_size, seq_len = P.seq_len, T = P.attn_tile, S = P.num_stages, SP = P.attn_split;
   float* q_s = ws;       // [hs] rotated query
   float* k_s = ws + hs;  // [hs] rotated key of the current position
   const int kvh = head / P.kv_mul;
   const size_t head_block = (static_cast<size_t>(ph.layer) * (P.kv_dim / hs) + kvh) * seq_len * hs;
   float* kcache = P.key_cache + head_block;
-  const float* vcache = P.value_cache + head_block;
-  // scores / probabilities: shared memory when the context fits the workspace (the ring leaves
-  // almost no L1), else the global [head][seq_len] buffer the reference uses
-  const int smem_cap = (P.xbuf_bytes >> 2) - 2 * hs;
-  float* score_head = (pos + 1 <= smem_cap) ? (ws + 2 * hs) : (P.score + static_cast<size_t>(head) * seq_len);
-
-  // value row of the current position (written by the QKV phase of this token)
-  const bool handoff = ph.tq != nullptr;  // q / k / v arrive as tagged words: no barrier before us
-  float v_pos = 0.f;
-  if (tid < hs)
-    v_pos = handoff ? poll_tagged(ph.tv + kvh * hs + tid, tag_in) : __ldcg(vcache + static_cast<size_t>(pos) * hs + tid);
+  unsigned long long* sc_out = P.scores + static_cast<size_t>(head) * seq_len;
+  const bool handoff = ph.tq != nullptr;  // q / k arrive as tagged words: no barrier before us
 
   // RoPE on q (this head) and on the new key row, rope_kernel.cu as compiled (elementwise.cu)
   if (tid < hs / 2) {
@@ -688,15 +692,17 @@ __device__ KLLM_PHASE_CALL Pipe attention_phase(const Params& P, int head, int p
     const float q1 = handoff ? poll_tagged(ph.tq + head * hs + i1, tag_in) : __ldcg(qg + i1);
     q_s[i0] = __fmaf_rn(fcr, q0, -__fmul_rn(fci, q1));
     q_s[i1] = __fmaf_rn(fci, q0, __fmul_rn(fcr, q1));
-    const float k0 = handoff ? poll_tagged(ph.tk + kvh * hs + i0, tag_in) : __ldcg(kg + i0);
-    const float k1 = handoff ? poll_tagged(ph.tk + kvh * hs + i1, tag_in) : __ldcg(kg + i1);
-    const float r0 = __fmaf_rn(fcr, k0, -__fmul_rn(fci, k1));
-    const float r1 = __fmaf_rn(fci, k0, __fmul_rn(fcr, k1));
-    k_s[i0] = r0;
-    k_s[i1] = r1;
-    if (head % P.kv_mul == 0) {  // one writer per kv head stores the rotated key
-      kcache[(static_cast<size_t>(i0 >> 2) * seq_len + pos) * 4 + (i0 & 3)] = r0;
-      kcache[(static_cast<size_t>(i1 >> 2) * seq_len + pos) * 4 + (i1 & 3)] = r1;
+    if (split == 0) {  // the new key row: one CTA of the head scores it, one CTA per kv head stores it
+      const float k0 = handoff ? poll_tagged(ph.tk + kvh * hs + i0, tag_in) : __ldcg(kg + i0);
+      const float k1 = handoff ? poll_tagged(ph.tk + kvh * hs + i1, tag_in) : __ldcg(kg + i1);
+      const float r0 = __fmaf_rn(fcr, k0, -__fmul_rn(fci, k1));
+      const float r1 = __fmaf_rn(fci, k0, __fmul_rn(fcr, k1));
+      k_s[i0] = r0;
+      k_s[i1] = r1;
+      if (head % P.kv_mul == 0) {
+        kcache[(static_cast<size_t>(i0 >> 2) * seq_len + pos) * 4 + (i0 & 3)] = r0;
+        kcache[(static_cast<size_t>(i1 >> 2) * seq_len + pos) * 4 + (i1 & 3)] = r1;
+      }
     }
   }
   consumer_sync<CT>();
@@ -705,7 +711,7 @@ __device__ KLLM_PHASE_CALL Pipe attention_phase(const Params& P, int head, int p
   const float scale = 1.f / sqrtf(static_cast<float>(hs));
   const float4* q4 = reinterpret_cast<const float4*>(q_s);
   const int n_tiles = attn_tiles(pos, T);
-  for (int j = 0; j < n_tiles; ++j) {
+  for (int j = split; j < n_tiles; j += SP) {
     const int t0 = j * T;
     const int nt = min(T, pos - t0);
     mbar_wait(&full_bar[pipe.slot], pipe.parity);
@@ -721,13 +727,13 @@ __device__ KLLM_PHASE_CALL Pipe attention_phase(const Params& P, int head, int p
         score = __fmaf_rn(kv.z, qv.z, score);
         score = __fmaf_rn(kv.w, qv.w, score);
       }
-      score_head[t0 + tid] = __fmul_rn(score, scale);
+      st_tagged_gpu(sc_out + t0 + tid, __fmul_rn(score, scale), tag_out);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
     pipe.advance(S);
   }
-  if (tid == 0) {  // t == pos from the freshly rotated key
+  if (split == 0 && tid == 0) {  // t == pos from the freshly rotated key
     const float4* k4 = reinterpret_cast<const float4*>(k_s);
     float score = 0.0f;
     for (int c = 0; c < (hs >> 2); ++c) {
@@ -738,7 +744,51 @@ __device__ KLLM_PHASE_CALL Pipe attention_phase(const Params& P, int head, int p
       score = __fmaf_rn(kv.z, qv.z, score);
       score = __fmaf_rn(kv.w, qv.w, score);
     }
-    score_head[pos] = __fmul_rn(score, scale);
+    st_tagged_gpu(sc_out + pos, __fmul_rn(score, scale), tag_out);
+  }
+  return pipe;
+}
+
+template <int CW>
+__device__ KLLM_PHASE_CALL Pipe attention_pv_phase(const Params& P, int head, int split, int pos, Pipe pipe,
+                                                   unsigned tag_scores, unsigned tag_qkv, unsigned tag_out) {
+  const Phase& ph = g_ph_cons;
+  float* ws = reinterpret_cast<float*>(smem);
+  float* s_warp = g_s_warp;
+  float* s_bcast = &g_s_bcast;
+  unsigned char* stages = smem + P.xbuf_bytes + P.xres_bytes;
+  uint64_t* full_bar = g_full_bar;
+  uint64_t* empty_bar = g_empty_bar;
+  constexpr int CT = CW * 32;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int hs = P.head_size, seq_len = P.seq_len, S = P.num_stages, SP = P.attn_split;
+  const int dv = hs / SP, T = P.attn_tile_v;
+  const int kvh = head / P.kv_mul;
+  const size_t slice_block =
+      ((static_cast<size_t>(ph.layer) * (P.kv_dim / hs) + kvh) * SP + split) * seq_len * dv;
+  const float* vslice = P.value_cache + slice_block;
+  const bool handoff = ph.tv != nullptr;
+  // scores / probabilities: shared memory when the context fits the workspace (the ring leaves
+  // almost no L1), else the global [head][seq_len] buffer the reference uses (the SP CTAs of a head
+  // then write identical values to it)
+  const int smem_cap = P.xbuf_bytes >> 2;
+  float* score_head = (pos + 1 <= smem_cap) ? ws : (P.score + static_cast<size_t>(head) * seq_len);
+
+  // this CTA's dv dims of the value row of the current position (written by the QKV phase of this token)
+  float v_pos = 0.f;
+  if (tid < dv)
+    v_pos = handoff ? poll_tagged(ph.tv + kvh * hs + split * dv + tid, tag_qkv)
+                    : __ldcg(vslice + static_cast<size_t>(pos) * dv + tid);
+
+  // all pos + 1 scaled scores of the head, polled in place
+  const int size = pos + 1;
+  {
+    const unsigned long long* sc_in = P.scores + static_cast<size_t>(head) * seq_len;
+    const int n4 = size >> 2;  // seq_len % 4 == 0: the head's words start 32-byte aligned
+    stage_handoff<4>(sc_in, tag_scores, n4, tid, CT, reinterpret_cast<float4*>(score_head));
+    const int rest = 4 * n4 + tid;
+    if (tid < 4 && rest < size) score_head[rest] = poll_tagged(sc_in + rest, tag_scores);
   }
   consumer_sync<CT>();
 
@@ -747,7 +797,6 @@ __device__ KLLM_PHASE_CALL Pipe attention_phase(const Params& P, int head, int p
   // elements tid + 256 k and tid + 128 + 256 k): the maximum does not care about order, and for the
   // sum each virtual thread keeps its own left-to-right partial, each virtual warp its own shuffle
   // tree (real warp q holds virtual warps q and q + 4), then the eight warp sums are added in order.
-  const int size = pos + 1;
   constexpr int kHalf = kSoftmaxThreads / 2;  // 128 real threads
   static_assert(CT >= kHalf, "softmax needs 128 consumer threads");
   const bool sm_thread = tid < kHalf;
@@ -794,26 +843,28 @@ __device__ KLLM_PHASE_CALL Pipe attention_phase(const Params& P, int head, int p
 
   // ---- weighted value sum, mha_kernel.cu:97-109: one FFMA chain per output element ----------------
   float value = 0.0f;
+  const int n_tiles = attn_tiles(pos, T);
   for (int j = 0; j < n_tiles; ++j) {
     const int t0 = j * T;
     const int nt = min(T, pos - t0);
     mbar_wait(&full_bar[pipe.slot], pipe.parity);
-    if (tid < hs) {
+    if (tid < dv) {
       const float* vt = reinterpret_cast<const float*>(stages + static_cast<size_t>(pipe.slot) * P.stage_bytes) + tid;
       const float* pr = score_head + t0;
 #pragma unroll 8
-      for (int tt = 0; tt < nt; ++tt) value = __fmaf_rn(pr[tt], vt[tt * hs], value);
+      for (int tt = 0; tt < nt; ++tt) value = __fmaf_rn(pr[tt], vt[tt * dv], value);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
     pipe.advance(S);
   }
-  if (tid < hs) {
+  if (tid < dv) {
     value = __fmaf_rn(score_head[pos], v_pos, value);
+    const int d = split * dv + tid;
     if (ph.ta != nullptr)
-      st_tagged_gpu(ph.ta + static_cast<size_t>(head) * hs + tid, value, tag_out);
+      st_tagged_gpu(ph.ta + static_cast<size_t>(head) * hs + d, value, tag_out);
     else
-      P.attn_out[static_cast<size_t>(head) * hs + tid] = value;
+      P.attn_out[static_cast<size_t>(head) * hs + d] = value;
   }
   return pipe;
 }
@@ -900,8 +951,8 @@ __device__ KLLM_STAGE_CALL float stage_exchange(const unsigned long long* area, 
 
 // Local hand-off (tag_in): the previous phase's output vector, polled in place.
 template <int UP>
-__device__ KLLM_STAGE_CALL void stage_handoff(const unsigned long long* src, unsigned tag, int n4, int t, int NT,
-                                              float4* xs4) {
+__device__ __forceinline__ void stage_handoff_inline(const unsigned long long* src, unsigned tag, int n4, int t, int NT,
+                                                     float4* xs4) {
   const long long t_start = clock64();
   for (int pb = t; pb < n4; pb += NT * UP) {
     unsigned long long wd[UP][4];
@@ -934,6 +985,11 @@ __device__ KLLM_STAGE_CALL void stage_handoff(const unsigned long long* src, uns
       if (p < n4) xs4[p] = make_float4(val_of(wd[k][0]), val_of(wd[k][1]), val_of(wd[k][2]), val_of(wd[k][3]));
     }
   }
+}
+template <int UP>
+__device__ KLLM_STAGE_CALL void stage_handoff(const unsigned long long* src, unsigned tag, int n4, int t, int NT,
+                                              float4* xs4) {
+  stage_handoff_inline<UP>(src, tag, n4, t, NT, xs4);
 }
 
 // ---- one GEMV phase of one CTA's consumer warps --------------------------------------------------
@@ -1098,9 +1154,10 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
     if (residual != nullptr) v = __fadd_rn(res_v, v);       // llama3.cpp:683,719: x + out
     if (sg.tag_out != nullptr) st_tagged_gpu(sg.tag_out + rr.row, v, hand_tag(ph.hand_out));
     if (sg.out == nullptr) {
-    } else if (sg.head_major) {
-      const int hs = P.head_size;
-      sg.out[(static_cast<size_t>(rr.row / hs) * P.seq_len + pos) * hs + rr.row % hs] = v;
+    } else if (sg.head_major) {  // value cache [kv_head][SP][seq_len][dv]
+      const int hs = P.head_size, dv = hs / P.attn_split;
+      const int kvh = rr.row / hs, d = rr.row % hs;
+      sg.out[((static_cast<size_t>(kvh) * P.attn_split + d / dv) * P.seq_len + pos) * dv + d % dv] = v;
     } else {
       sg.out[static_cast<long long>(pos) * sg.pos_stride + rr.row] = v;
     }
@@ -1297,10 +1354,11 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
           __syncwarp();
         }
         const Phase& ph = s_phase_prod;
-        if (ph.kind == kPhaseAttention) {
-          if (cta >= P.head_num || ppos == 0) continue;
+        if (ph.kind == kPhaseAttention || ph.kind == kPhaseAttnPV) {
+          const int SP = P.attn_split;
+          if (cta >= P.head_num * SP || ppos == 0) continue;
           // rows t < pos of this head: final since the previous token.  Order the async-proxy
-          // reads after the grid barrier that closed the previous token's attention phase.
+          // reads after the grid barrier that closed the previous token.
           if (tok > 0 && lane == 0) {
             const unsigned need = P.barrier_base +
                                   static_cast<unsigned>((tok - 1) * P.bars_per_token + ph.barrier_idx) *
@@ -1310,30 +1368,44 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
             asm volatile("fence.proxy.async;" ::: "memory");
           }
           __syncwarp();
-          const int hs = P.head_size, T = P.attn_tile;
-          const int kvh = cta / P.kv_mul;
+          const int hs = P.head_size;
+          const int head = cta / SP, split = cta % SP;
+          const int kvh = head / P.kv_mul;
           const size_t head_block =
               (static_cast<size_t>(ph.layer) * (P.kv_dim / hs) + kvh) * P.seq_len * hs;
-          const float* kbase = P.key_cache + head_block;
-          const float* vbase = P.value_cache + head_block;
-          const int n_tiles = attn_tiles(ppos, T);
-          for (int kv = 0; kv < 2; ++kv) {
-            for (int j = 0; j < n_tiles; ++j) {
+          if (ph.kind == kPhaseAttention) {  // K tiles j = split, split + SP, ...
+            const int T = P.attn_tile;
+            const float* kbase = P.key_cache + head_block;
+            const int n_tiles = attn_tiles(ppos, T);
+            for (int j = split; j < n_tiles; j += SP) {
               const int t0 = j * T;
               const int nt = min(T, ppos - t0);
               mbar_wait(&empty_bar[pipe.slot], pipe.parity ^ 1u);
               unsigned char* dst = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
               if (lane == 0) mbar_expect_tx(&full_bar[pipe.slot], static_cast<uint32_t>(nt) * hs * 4);
               __syncwarp();
-              if (kv == 0) {
-                if (lane < (hs >> 2))  // hs <= 128 (checked on the host): one 16-byte chunk column per lane
-                  bulk_g2s(dst + static_cast<size_t>(lane) * T * 16,
-                           kbase + (static_cast<size_t>(lane) * P.seq_len + t0) * 4,
-                           static_cast<uint32_t>(nt) * 16, &full_bar[pipe.slot], policy_kv);
-              } else if (lane == 0) {
-                bulk_g2s(dst, vbase + static_cast<size_t>(t0) * hs, static_cast<uint32_t>(nt) * hs * 4,
+              if (lane < (hs >> 2))  // hs <= 128 (checked on the host): one 16-byte chunk column per lane
+                bulk_g2s(dst + static_cast<size_t>(lane) * T * 16,
+                         kbase + (static_cast<size_t>(lane) * P.seq_len + t0) * 4,
+                         static_cast<uint32_t>(nt) * 16, &full_bar[pipe.slot], policy_kv);
+              pipe.advance(S);
+              if (lane == 0) s_fill_count = ++filled; else ++filled;
+            }
+          } else {  // this CTA's slice of V: [seq_len][dv] contiguous
+            const int dv = hs / SP, T = P.attn_tile_v;
+            const float* vbase = P.value_cache + head_block + static_cast<size_t>(split) * P.seq_len * dv;
+            const int n_tiles = attn_tiles(ppos, T);
+            for (int j = 0; j < n_tiles; ++j) {
+              const int t0 = j * T;
+              const int nt = min(T, ppos - t0);
+              mbar_wait(&empty_bar[pipe.slot], pipe.parity ^ 1u);
+              unsigned char* dst = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
+              if (lane == 0) {
+                mbar_expect_tx(&full_bar[pipe.slot], static_cast<uint32_t>(nt) * dv * 4);
+                bulk_g2s(dst, vbase + static_cast<size_t>(t0) * dv, static_cast<uint32_t>(nt) * dv * 4,
                          &full_bar[pipe.slot], policy_kv);
               }
+              __syncwarp();
               pipe.advance(S);
               if (lane == 0) s_fill_count = ++filled; else ++filled;
             }
@@ -1421,8 +1493,12 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
           __syncwarp();
         }
         const Phase& ph = s_phase_pf;
-        if (ph.kind == kPhaseAttention) {  // KV tiles are L2-resident already (evict_last): count only
-          if (cta < P.head_num && ppos > 0) ahead += 2u * static_cast<unsigned>(attn_tiles(ppos, P.attn_tile));
+        if (ph.kind == kPhaseAttention || ph.kind == kPhaseAttnPV) {
+          // KV tiles are L2-resident already (evict_last): count the producer's ring stages only
+          if (cta < P.head_num * P.attn_split && ppos > 0)
+            ahead += ph.kind == kPhaseAttention
+                         ? static_cast<unsigned>(own_tiles(attn_tiles(ppos, P.attn_tile), cta % P.attn_split, P.attn_split))
+                         : static_cast<unsigned>(attn_tiles(ppos, P.attn_tile_v));
           continue;
         }
         const int u0 = static_cast<int>(static_cast<long long>(cta) * ph.units / G);
@@ -1511,8 +1587,15 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
           (PROF && prof_on) ? P.prof + (static_cast<size_t>(cta) * P.n_phases + pi) * kProfStamps : nullptr;
       if (stamp) stamp[0] = global_ns();
 
-      if (ph.kind == kPhaseAttention) {
-        if (cta < P.head_num) pipe = attention_phase<CW>(P, cta, pos, pipe, hand_tag(ph.hand_in), hand_tag(ph.hand_out));
+      if (ph.kind == kPhaseAttention || ph.kind == kPhaseAttnPV) {
+        const int SP = P.attn_split;
+        if (cta < P.head_num * SP) {
+          if (ph.kind == kPhaseAttention)
+            pipe = attention_scores_phase<CW>(P, cta / SP, cta % SP, pos, pipe, hand_tag(ph.hand_in), hand_tag(ph.hand_out));
+          else
+            pipe = attention_pv_phase<CW>(P, cta / SP, cta % SP, pos, pipe, hand_tag(ph.hand_in), hand_tag(ph.hand_aux),
+                                          hand_tag(ph.hand_out));
+        }
         if (stamp) stamp[1] = stamp[2] = global_ns();
         if (ph.barrier_after) grid_barrier<CT>(P.barrier, bar_target, G);
         prev_barrier = ph.barrier_after != 0;
@@ -1662,6 +1745,19 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   stages_ = stages;
   attn_tile_ = std::min(stage_bytes / (hs * 4), consumer_warps_ * 32) & ~31;  // one timestep per consumer thread
   if (attn_tile_ < 32) return KLLM_E_UNSUPPORTED;
+  // attention split: SP CTAs per query head (power of two, <= 8), each owning head_size / SP output dims
+  // (a multiple of 4 floats so that V slice rows stay 16-byte units for the bulk copies)
+  if (m.seq_len & 3) return KLLM_E_UNSUPPORTED;
+  attn_split_ = 1;
+  while (attn_split_ * 2 <= 8 && m.head_num * attn_split_ * 2 <= grid_ && (hs / (attn_split_ * 2)) % 4 == 0 &&
+         hs % (attn_split_ * 2) == 0)
+    attn_split_ *= 2;
+  if (const char* e = getenv("KLLM_ATTN_SPLIT")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= attn_split_ && (v & (v - 1)) == 0) attn_split_ = v;
+  }
+  attn_tile_v_ = (stage_bytes / ((hs / attn_split_) * 4)) & ~31;
+  if (attn_tile_v_ < 32) return KLLM_E_UNSUPPORTED;
   xbuf_bytes_ = xbuf;
   xres_bytes_ = xres;
   smem_bytes_ = static_cast<size_t>(mega::kCtlBytes) + xbuf + xres + static_cast<size_t>(stages) * stage_bytes;
@@ -1716,6 +1812,12 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       return static_cast<int>(cudaErrorMemoryAllocation);
     cudaMemsetAsync(d_handoff_, 0, sizeof(unsigned long long) * words, stream);
     t_q = d_handoff_, t_k = t_q + q_rows, t_v = t_k + kvd, t_attn = t_v + kvd, t_h = t_attn + q_rows;
+  }
+  {
+    const size_t words = static_cast<size_t>(m.head_num) * m.seq_len;
+    if (cudaMalloc(&d_scores_, sizeof(unsigned long long) * words) != cudaSuccess)
+      return static_cast<int>(cudaErrorMemoryAllocation);
+    cudaMemsetAsync(d_scores_, 0, sizeof(unsigned long long) * words, stream);
   }
   int hands = 0;
   if (tagged_ && W == 1) {
@@ -1782,13 +1884,28 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       close_phase(p, !handoffs);
       ph.push_back(p);
     }
-    {
+    int qkv_hand = 0;
+    {  // attention, scores: CTA (head, s) scores the K tiles s, s + SP, ... and publishes them tagged
       Phase p{};
       p.kind = mega::kPhaseAttention;
       p.layer = l;
       if (handoffs) {
-        p.tq = t_q, p.tk = t_k, p.tv = t_v, p.ta = t_attn;
+        p.tq = t_q, p.tk = t_k, p.tv = t_v;
         p.hand_in = hands++;
+      }
+      qkv_hand = p.hand_in;
+      p.hand_out = hands;  // the scores (always tagged words, also in the barrier modes)
+      close_phase(p, !handoffs);
+      ph.push_back(p);
+    }
+    {  // attention, softmax + P.V: CTA (head, s) owns output dims [s dv, (s + 1) dv)
+      Phase p{};
+      p.kind = mega::kPhaseAttnPV;
+      p.layer = l;
+      p.hand_in = hands++;
+      if (handoffs) {
+        p.tv = t_v, p.ta = t_attn;
+        p.hand_aux = qkv_hand;
         p.hand_out = hands;
       }
       close_phase(p, !handoffs);
@@ -1871,7 +1988,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   // The producer streams K/V rows written by the PREVIOUS token once the grid barrier that closed
   // that token's attention phase is passed; without such a barrier, the one that closed the token.
   for (Phase& p : ph)
-    if (p.kind == mega::kPhaseAttention && !p.barrier_after) p.barrier_idx = bars;
+    if ((p.kind == mega::kPhaseAttention || p.kind == mega::kPhaseAttnPV) && !p.barrier_after) p.barrier_idx = bars;
 
   if (cudaMalloc(&d_phases_, sizeof(Phase) * ph.size()) != cudaSuccess) return static_cast<int>(cudaErrorMemoryAllocation);
   cudaMemcpyAsync(d_phases_, ph.data(), sizeof(Phase) * ph.size(), cudaMemcpyHostToDevice, stream);
@@ -1903,6 +2020,8 @@ void MegaEngine::destroy() {
   if (d_arg_idx_) cudaFree(d_arg_idx_);
   if (d_tagged_) cudaFree(d_tagged_);
   if (d_handoff_) cudaFree(d_handoff_);
+  if (d_scores_) cudaFree(d_scores_);
+  d_scores_ = nullptr;
   d_handoff_ = nullptr;
   d_tagged_ = nullptr;
   d_phases_ = nullptr;
@@ -1927,6 +2046,9 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
   P.xbuf_bytes = xbuf_bytes_;
   P.xres_bytes = xres_bytes_;
   P.attn_tile = attn_tile_;
+  P.attn_tile_v = attn_tile_v_;
+  P.attn_split = attn_split_;
+  P.scores = d_scores_;
   P.pf_stages = 8;  // 8 x 32 KB x 148 SMs = 38 MB of weights in flight towards L2 (measured: 6-12 best, >=24 thrashes L2)
   if (const char* e = getenv("KLLM_PREFETCH_STAGES")) P.pf_stages = std::max(0, atoi(e));
   P.group_size = m.group_size;

@@ -8,7 +8,7 @@
 namespace kllm {
 namespace mega {
 
-enum { kPhaseGemv = 0, kPhaseAttention = 1 };
+enum { kPhaseGemv = 0, kPhaseAttention = 1 /* scores of the split attention */, kPhaseAttnPV = 2 /* softmax + P.V */ };
 constexpr int kProfStamps = 16;  // uint64 stamps per (CTA, phase) of kllm_decoder_profile
 
 struct Seg {
@@ -67,6 +67,7 @@ struct Phase {
   const unsigned long long* tv;
   unsigned long long* ta;
   int hand_in, hand_out;
+  int hand_aux;           // attention P.V phase: the q|k|v hand-off (value row of the current position)
   Seg seg[3];
 };
 
@@ -81,7 +82,10 @@ struct Params {
   int skip_cls_tokens;  // the first skip_cls_tokens positions of this launch are prompt tokens: no classifier pass
   int num_stages, stage_bytes, xbuf_bytes;
   int xres_bytes;  // shared-memory copy of the residual stream behind the input vector (tagged modes; else 0)
-  int attn_tile;  // timesteps per K/V ring stage
+  int attn_tile;    // timesteps per K ring stage
+  int attn_tile_v;  // timesteps per V ring stage (rows of head_size / attn_split floats)
+  int attn_split;   // CTAs per query head: K tiles round-robin, P.V output dims split (bit-exact chains)
+  unsigned long long* scores;  // [head][seq_len] tagged scaled scores: scores phase -> P.V phase
   int pf_stages;  // L2 prefetch run-ahead of the ring producer, in ring stages (0 = off)
   int group_size;
   int dim, vocab_size, head_num, head_size, kv_dim, kv_mul, seq_len, flavour;
@@ -91,7 +95,7 @@ struct Params {
   float* attn_out;
   float* score;
   // KV cache in the persistent engine's own layout (see megakernel.cu "KV layout"):
-  //   K [L][kv_head][head_size/4][seq_len][4]    V [L][kv_head][seq_len][head_size]
+  //   K [L][kv_head][head_size/4][seq_len][4]    V [L][kv_head][attn_split][seq_len][head_size/attn_split]
   float* key_cache;
   const float* value_cache;
   const float* sin_cache;
@@ -161,6 +165,7 @@ class MegaEngine {
   int stage_bytes() const { return stage_bytes_; }
   int phases() const { return n_phases_; }
   int attn_tile() const { return attn_tile_; }
+  int attn_split() const { return attn_split_; }
   int consumer_warps() const { return consumer_warps_; }
   bool int8_fast() const { return int8_fast_ != 0; }
 
@@ -179,6 +184,8 @@ class MegaEngine {
   unsigned tp_seq_base_ = 0, hand_base_ = 0;
   int grid_ = 0, stages_ = 0, stage_bytes_ = 0, xbuf_bytes_ = 0, xres_bytes_ = 0, n_phases_ = 0, attn_tile_ = 0;
   int consumer_warps_ = 8, threads_ = 0;
+  int attn_split_ = 1, attn_tile_v_ = 0;
+  unsigned long long* d_scores_ = nullptr;  // tagged scores of the split attention
   int int8_fast_ = 0;
   const void* kernel_ = nullptr;       // decode_megakernel<consumer warps, int8, false>
   const void* kernel_prof_ = nullptr;  // ... <.., true>: records the phase timeline stamps

@@ -84,15 +84,18 @@ __global__ void swiglu_rows_kernel(float* __restrict__ h1, const float* __restri
 }
 
 struct CacheLayout {
-  int mega;  // 1: persistent engine K [kvh][hs/4][seq][4], V [kvh][seq][hs]; 0: [seq][kv_dim]
-  int seq_len, kv_dim, head_size;
+  int mega;  // 1: persistent engine K [kvh][hs/4][seq][4], V [kvh][split][seq][hs/split]; 0: [seq][kv_dim]
+  int seq_len, kv_dim, head_size, split;
 };
 __device__ __forceinline__ size_t k_index(const CacheLayout& c, int pos, int kvh, int i) {
   if (c.mega) return (static_cast<size_t>(kvh) * (c.head_size >> 2) + (i >> 2)) * c.seq_len * 4 + static_cast<size_t>(pos) * 4 + (i & 3);
   return static_cast<size_t>(pos) * c.kv_dim + kvh * c.head_size + i;
 }
 __device__ __forceinline__ size_t v_index(const CacheLayout& c, int pos, int kvh, int i) {
-  if (c.mega) return (static_cast<size_t>(kvh) * c.seq_len + pos) * c.head_size + i;
+  if (c.mega) {
+    const int dv = c.head_size / c.split;
+    return ((static_cast<size_t>(kvh) * c.split + i / dv) * c.seq_len + pos) * dv + i % dv;
+  }
   return static_cast<size_t>(pos) * c.kv_dim + kvh * c.head_size + i;
 }
 
@@ -190,7 +193,7 @@ int prefill_block(const PrefillModel& m, PrefillWorkspace& ws, const int32_t* to
   const int ew_grid = 592;  // 4 x 148 SMs for the grid-stride elementwise kernels
   embed_rows_kernel<<<T, 256, 0, s>>>(tokens_dev, m.tok_emb, ws.x, dim, m.vocab_size);
   PF_TRY(count());
-  const CacheLayout cl{m.mega_layout, m.seq_len, kvd, hs};
+  const CacheLayout cl{m.mega_layout, m.seq_len, kvd, hs, m.attn_split > 0 ? m.attn_split : 1};
   for (int l = 0; l < m.layer_num; ++l) {
     const size_t layer_off = static_cast<size_t>(l) * m.seq_len * kvd;
     rmsnorm_rows_kernel<<<T, 256, 0, s>>>(ws.x, m.attn_norm[l], ws.xn, dim, m.eps);

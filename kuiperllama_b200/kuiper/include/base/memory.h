@@ -41,6 +41,34 @@ class DeviceAllocator {
   DeviceType device_type_ = DeviceType::kDeviceUnknown;
 };
 
+// Host -> device staging for checkpoint uploads.  The reference copies every weight straight out of
+// the pageable mmap with a blocking cudaMemcpy (tensor.cpp:104-119 via alloc.cpp:14-38), which the
+// driver serialises through its own bounce buffer: page faults, the host copy and the DMA take turns.
+// Here large copies go through two pinned buffers: while the copy engine drains one, the host fills
+// the other from the mapping (page-cache reads overlap the DMA).  One instance per process; copies of
+// less than kMinBytes, and everything after a failed pinned allocation, take the plain path.
+class PinnedUploader {
+ public:
+  static constexpr size_t kChunkBytes = size_t(32) << 20;
+  static constexpr size_t kMinBytes = size_t(1) << 20;
+  static PinnedUploader& instance();
+  ~PinnedUploader();
+  // enqueue host -> device on `stream`; returns false if the pinned path is unavailable
+  bool upload(void* dst_device, const void* src_host, size_t bytes, void* stream);
+  size_t bytes_uploaded() const { return uploaded_; }
+
+ private:
+  PinnedUploader() = default;
+  bool ensure();
+  void* pinned_[2] = {nullptr, nullptr};
+  void* done_[2] = {nullptr, nullptr};  // cudaEvent_t: the DMA out of pinned_[i] has finished
+  bool busy_[2] = {false, false};
+  int next_ = 0;
+  bool failed_ = false;
+  size_t uploaded_ = 0;
+  std::mutex mu_;
+};
+
 class CPUDeviceAllocator final : public DeviceAllocator {
  public:
   CPUDeviceAllocator() : DeviceAllocator(DeviceType::kDeviceCPU) {}

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime_api.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -37,6 +38,9 @@ void DeviceAllocator::memcpy(const void* src_ptr, void* dest_ptr, size_t byte_si
   if (byte_size == 0) return;
   if (memcpy_kind == MemcpyKind::kMemcpyCPU2CPU) {
     std::memcpy(dest_ptr, src_ptr, byte_size);
+  } else if (memcpy_kind == MemcpyKind::kMemcpyCPU2CUDA && stream != nullptr && byte_size >= PinnedUploader::kMinBytes &&
+             PinnedUploader::instance().upload(dest_ptr, src_ptr, byte_size, stream)) {
+    // checkpoint-sized host -> device copy: pinned, double-buffered (see PinnedUploader)
   } else {
     cudaError_t e;
     if (stream != nullptr) {
@@ -48,6 +52,52 @@ void DeviceAllocator::memcpy(const void* src_ptr, void* dest_ptr, size_t byte_si
     CHECK(e == cudaSuccess) << "memcpy failed: " << cudaGetErrorString(e);
   }
   if (need_sync) cudaDeviceSynchronize();
+}
+
+// ---- PinnedUploader ------------------------------------------------------------------------------------
+PinnedUploader& PinnedUploader::instance() {
+  static PinnedUploader u;
+  return u;
+}
+bool PinnedUploader::ensure() {
+  if (failed_) return false;
+  if (pinned_[0] != nullptr) return true;
+  for (int i = 0; i < 2; ++i) {
+    cudaEvent_t ev = nullptr;
+    if (cudaMallocHost(&pinned_[i], kChunkBytes) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+      failed_ = true;
+      cudaGetLastError();
+      return false;
+    }
+    done_[i] = ev;
+  }
+  return true;
+}
+bool PinnedUploader::upload(void* dst_device, const void* src_host, size_t bytes, void* stream) {
+  std::lock_guard<std::mutex> lock(mu_);
+  if (!ensure()) return false;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const char* src = static_cast<const char*>(src_host);
+  char* dst = static_cast<char*>(dst_device);
+  for (size_t off = 0; off < bytes; off += kChunkBytes) {
+    const size_t n = std::min(kChunkBytes, bytes - off);
+    const int b = next_;
+    next_ ^= 1;
+    if (busy_[b]) cudaEventSynchronize(static_cast<cudaEvent_t>(done_[b]));  // its previous DMA has drained
+    std::memcpy(pinned_[b], src + off, n);  // page faults + host copy overlap the other buffer's DMA
+    if (cudaMemcpyAsync(dst + off, pinned_[b], n, cudaMemcpyHostToDevice, s) != cudaSuccess) return false;
+    cudaEventRecord(static_cast<cudaEvent_t>(done_[b]), s);
+    busy_[b] = true;
+  }
+  uploaded_ += bytes;
+  return true;
+}
+PinnedUploader::~PinnedUploader() {
+  for (int i = 0; i < 2; ++i) {
+    if (done_[i]) cudaEventDestroy(static_cast<cudaEvent_t>(done_[i]));
+    if (pinned_[i]) cudaFreeHost(pinned_[i]);
+  }
 }
 
 void DeviceAllocator::memset_zero(void* ptr, size_t byte_size, void* stream, bool need_sync) {

@@ -94,8 +94,8 @@ def _gloo_rank(rank, world, key, steps, out_dir):
     np.savez(f"{out_dir}/rank{rank}.npz", ids=np.array(ids), logits=logits)
 
 
-@pytest.mark.parametrize("key,world", [("small-tp", 2), ("small-tp", 4), ("small-int8", 2), ("small-tp-int8", 2),
-                                       ("small-qwen", 2)])
+@pytest.mark.parametrize("key,world", [("small-tp", 2), ("small-tp", 4), ("small-tp", 8), ("small-int8", 2),
+                                       ("small-tp-int8", 2), ("small-qwen", 2)])
 def test_gloo_tensor_parallel_decode_matches_unsharded_oracle(oracle, tmp_path, key, world):
     from kuiperllama_b200.checkpoint import write_checkpoint
     steps = 12
@@ -209,7 +209,7 @@ TP_MODES = [("peer", "persistent"), ("peer", "graph"), ("nccl", "graph")]
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("key,world", [("small-tp", 2), ("small-int8", 2), ("small-tp-int8", 2), ("small-qwen", 2),
-                                       ("small-tp", 4)])
+                                       ("small-tp", 4), ("small-tp", 8)])  # world 8: 8 heads / 2 kv heads -> kv heads replicated
 def test_tp_decoder_matches_unsharded_oracle(kllm_lib, oracle, tmp_path, key, world):
     from kuiperllama_b200.checkpoint import write_checkpoint
     _need_gpus(world)

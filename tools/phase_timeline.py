@@ -41,7 +41,8 @@ def main():
     L = shape.layer_num
     print(f"# {shape.name}: phase timeline of the decode step at pos {a.pos} (us, globaltimer), grid {G}, {P} phases")
     print(f"# token time (first phase entered -> last barrier passed): {st[:, -1, 3].max():.1f} us")
-    names = ["qkv", "attn", "wo", "w1w3", "w2"]
+    names = ["qkv", "scores", "attn_pv", "wo", "w1w3", "w2"]
+    NPL = len(names)  # phases per layer
     stage = (st[:, :, 1] - st[:, :, 0])          # input staging (+norm)
     work = (st[:, :, 2] - st[:, :, 1])           # consuming ring stages (or attention)
     bar = (st[:, :, 3] - st[:, :, 2])            # waiting at the grid barrier
@@ -57,14 +58,15 @@ def main():
               f"{work[:, idx].max(axis=0).mean():9.2f} {bar[:, idx].min(axis=0).mean():11.2f} {np.median(bar[:, idx]):11.2f} | "
               f"{'':32s}{c[4]:8.2f} {c[1]:6.2f} {c[2]:6.2f} {c[3]:6.2f} {c[0]:6.2f}")
     for k, nm in enumerate(names):
-        row(nm, [l * 5 + k for l in range(L)])
+        row(nm, [l * NPL + k for l in range(L)])
     row("cls", [P - 1])
     # with tagged hand-overs most phases have no barrier: `barrier_*` is then ~0 and the wait for the
     # previous phase's outputs shows up in `stage_x` of the consuming phase (the poll loop)
     heads = shape.head_num
-    ai = [l * 5 + 1 for l in range(L)]
-    attn = (st[:heads, ai, 2] - st[:heads, ai, 0])
-    print(f"# attention on the {heads} head CTAs: median {np.median(attn):.2f} us, slowest head per layer (mean) "
+    ai = [l * NPL + 1 for l in range(L)]
+    pvi = [l * NPL + 2 for l in range(L)]
+    attn = (st[:heads, pvi, 2] - st[:heads, ai, 0])
+    print(f"# attention (scores + softmax + P.V) on the first {heads} attention CTAs: median {np.median(attn):.2f} us, slowest head per layer (mean) "
           f"{attn.max(axis=0).mean():.2f} us")
     print(f"# sum of phase durations: {dur.sum():.1f} us; barrier_min = time the LAST arriving CTA spends in the barrier")
 
