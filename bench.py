@@ -80,6 +80,11 @@ def parse_args():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOAD_NAMES),
                     help="default: tinyllama-1.1b on a single-GPU box at --gpus 1, else llama2-7b-int8")
     ap.add_argument("--reps", type=int, default=5, help="repetitions of the timed region; the median is reported")
+    ap.add_argument("--numerics", default="fast", choices=["fast", "exact"],
+                    help="fast (default): toleranced mode, |dlogit| <= 1e-4 vs the reference (tests/test_decoder_gpu.py); "
+                         "exact: every reduction in the reference's order, bit-identical logits.  The fast line "
+                         "carries the exact mode's numbers under \"exact\"")
+    ap.add_argument("--no-exact", action="store_true", help="skip the exact-mode leg of a --numerics fast run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="N>1: skip the fp32 Llama-2-7B line (configs[4])")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
@@ -287,7 +292,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": res["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_reference_cuda(args, rank, world):
@@ -303,8 +308,8 @@ def run_reference_cuda(args, rank, world):
     shape = SHAPES[args.workload]
     base = {"impl": "reference-cuda", "metric": METRIC, "unit": "tokens/s", "n_gpus": 1}
     if not REF_SO.exists() or shape.flavour != "llama2":
-        print(json.dumps({**base, "unavailable": "oracle/_ref has no model build for this workload "
-                          "(QWEN2 flavour needs absl/re2 for its tokenizer)" if REF_SO.exists() else "oracle/_ref not built"}))
+        emit({**base, "unavailable": "oracle/_ref has no model build for this workload "
+                          "(QWEN2 flavour needs absl/re2 for its tokenizer)" if REF_SO.exists() else "oracle/_ref not built"})
         return
     w = synth_weights(shape, "cuda", args.seed)
     path = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", f"kllm_refcuda_{os.getpid()}.bin")
@@ -329,12 +334,21 @@ def run_reference_cuda(args, rank, world):
     finally:
         if os.path.exists(path):
             os.remove(path)
-    print(json.dumps({**base, "value": K / dt, "steps": K, "ms_per_step": dt / K * 1e3, "higher_is_better": True,
+    emit({**base, "value": K / dt, "steps": K, "ms_per_step": dt / K * 1e3, "higher_is_better": True,
                       "dtype": "f32" if shape.group_size == 0 else "int8w/f32",
                       "config": {"workload": WORKLOAD_NAMES[args.workload], "shape": shape.name, "context": f"1->{K}",
                                  "batch": 1, "what": "the reference's own CUDA backend (kuiper/source/op/kernels/cuda/*.cu "
                                  "+ model/llama3.cpp, unmodified, nvcc 12.9 sm_100a) on this GPU, wall clock of the predict loop"},
-                      "roofline_frac_of_measured_hbm": shape.weight_bytes_per_token() * K / dt / 1e9 / measured_peaks()[0]}))
+                      "roofline_frac_of_measured_hbm": shape.weight_bytes_per_token() * K / dt / 1e9 / measured_peaks()[0]})
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def _leave_process_group():
@@ -352,7 +366,7 @@ def _leave_process_group():
 class Bench:
     """One workload on `world` GPUs: build, pre-pass, timed windows, e2e, per-position numbers."""
 
-    def __init__(self, args, rank, world, workload, stream, lib):
+    def __init__(self, args, rank, world, workload, stream, lib, numerics=None):
         import torch
         from kuiperllama_b200 import SHAPES, Decoder, synth_weights
         self.torch, self.args, self.rank, self.world, self.workload, self.lib = torch, args, rank, world, workload, lib
@@ -363,19 +377,20 @@ class Bench:
         self.comm = None
         self.local = shape
         self.parity = None
+        self.numerics = numerics = numerics or args.numerics
         if world > 1:
             import torch.distributed as dist
             from kuiperllama_b200.tensor_parallel import Comm, local_shape, make_tp_decoder
             self.comm = Comm(shape.dim)
             full = synth_weights(shape, "cuda", seed)  # same seed on every rank -> same model
-            self.dec = make_tp_decoder(shape, full, self.comm, stream.cuda_stream)
+            self.dec = make_tp_decoder(shape, full, self.comm, stream.cuda_stream, numerics=numerics)
             self.w, self.local = self.dec.weights, local_shape(shape, world, rank)
             self.parity = self._tp_parity(full, dist)
             del full
             torch.cuda.empty_cache()
         else:
             self.w = synth_weights(shape, "cuda", seed)
-            self.dec = Decoder(shape, self.w, stream=stream.cuda_stream)
+            self.dec = Decoder(shape, self.w, stream=stream.cuda_stream, numerics=numerics)
         self.engine = self.dec.engine
         self.launches_per_step = self.dec.launches_per_step
 
@@ -395,7 +410,7 @@ class Bench:
         torch = self.torch
         toks, ref_logits, ref_ids = [1], [], []
         if self.rank == 0:
-            one = Decoder(self.shape, full, stream=self.stream.cuda_stream)
+            one = Decoder(self.shape, full, stream=self.stream.cuda_stream, numerics="exact")
             tok = 1
             for pos in range(steps):
                 nxt = one.step(tok, pos)
@@ -417,7 +432,8 @@ class Bench:
                 top2 = np.sort(ref_logits[pos])[-2:]
                 if top2[1] - top2[0] > 2 * tol and nxt != ref_ids[pos]:
                     ids_ok = False
-        res = {"checked_against": "unsharded single-GPU decoder, same weights, teacher-forced", "steps": steps,
+        res = {"checked_against": "unsharded single-GPU decoder in exact (bit-identical-to-reference) numerics, same weights, "
+                                  "teacher-forced", "numerics": self.numerics, "steps": steps,
                "max_abs_logit_diff": worst, "tolerance": tol, "ids_equal_where_margin_gt_2e-4": ids_ok}
         if self.rank == 0 and (worst > tol or not ids_ok):
             raise SystemExit(f"tensor-parallel decode differs from the unsharded decoder: {res}")
@@ -580,7 +596,12 @@ def run_ours(args, rank, world):
                        "parallelism": "single GPU" if world == 1 else f"tp{world}",
                        "l2": "no flush: every step streams %.2f GB of weights per GPU >> 126 MB L2" % (res["bytes_gpu"] / 1e9),
                        "weight_bytes_per_token": res["bytes_tok"], "launches_per_step": b.launches_per_step,
-                       "engine": b.engine},
+                       "engine": b.engine,
+                       "numerics": "fast: free summation order (int8 rows on dp4a with 24-bit fixed-point activations, "
+                                   "flash-decoding attention), logits within 1e-4 of the exact mode "
+                                   "(tests/test_decoder_gpu.py::test_fast_numerics_within_north_star_tolerance); "
+                                   "exact-mode numbers under \"exact\"" if b.numerics == "fast" else
+                                   "exact: every reduction in the reference's order, logits bit-identical to the reference's CUDA path"},
             "e2e": res["e2e"],
             "by_position_tok_s": res["by_position_tok_s"],
             # kernels of libkllm_b200 launched inside ONE repetition of the timed region: the persistent
@@ -594,9 +615,23 @@ def run_ours(args, rank, world):
             line["config"]["weight_bytes_per_token_per_gpu"] = res["bytes_gpu"]
             line["parity"] = b.parity
     w_cpu = b.w if (world == 1 and not args.no_cpu_baseline) else None
+    primary_numerics = b.numerics
     b.close()
     del b
     torch.cuda.empty_cache()
+
+    if primary_numerics == "fast" and not args.no_exact:
+        # the verification mode on the same workload: bit-identical to the reference, reported next to the headline
+        xargs = argparse.Namespace(**{**vars(args), "reps": min(args.reps, 3)})
+        xb = Bench(xargs, rank, world, args.workload, stream, lib, numerics="exact")
+        xres = xb.run()
+        if rank == 0:
+            line["exact"] = {"value": xres["value"], "unit": "tokens/s", "ms_per_step": xres["ms_per_step"],
+                             "e2e": xres["e2e"], "by_position_tok_s": xres["by_position_tok_s"],
+                             "roofline_frac": xres["roofline"]["frac"], "parity": xb.parity}
+        xb.close()
+        del xb
+        torch.cuda.empty_cache()
 
     if world > 1 and not args.no_secondary and args.workload != "llama2-7b":
         # BASELINE.json configs[4]: the fp32 Llama-2-7B under the same tensor parallelism
@@ -614,14 +649,18 @@ def run_ours(args, rank, world):
     if rank == 0 and w_cpu is not None:
         line["cpu_baseline"] = cpu_reference_run(shape, w_cpu, 256, args.cpu_seconds)
     if rank == 0:
-        print(json.dumps(line))
-        sys.stdout.flush()
+        emit(line)
     if world > 1:
         _leave_process_group()
 
 
 def main():
     args = parse_args()
+    # ONE JSON line on stdout: libraries that chat on fd 1 (NCCL prints its version there) go to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world != args.gpus and world > 1:

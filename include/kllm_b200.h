@@ -203,10 +203,24 @@ typedef struct {
   /* preferred over the callback when set: the decoder then uses the fused
    * all-reduce + residual add of kllm_comm_allreduce_residual */
   kllm_comm* comm;
+  /* Numerics of the persistent engine.  KLLM_NUMERICS_EXACT (0, the default of a zeroed struct): every
+   * reduction in the reference's order -- logits and ids bit-identical to the reference's CUDA path
+   * (the verification mode).  KLLM_NUMERICS_FAST (1): free summation order where it buys speed --
+   * int8 rows as fixed-point activations x int8 weights on dp4a, attention as flash-decoding (split by
+   * timestep, online softmax) -- within the north-star tolerance (|dlogit| <= 1e-4, same greedy ids
+   * where the top-2 margin exceeds 2e-4; tests/test_decoder_gpu.py).  Environment KLLM_MODE=exact|fast
+   * overrides this field at create time. */
+  int32_t numerics;
 } kllm_decoder_desc;
+#define KLLM_NUMERICS_EXACT 0
+#define KLLM_NUMERICS_FAST 1
 
 typedef struct kllm_decoder kllm_decoder;
 
+/* `stream`: the cudaStream_t every launch and copy of this decoder is ordered on.  NULL = the decoder
+ * creates a private non-blocking stream and device-synchronises once here, so weights uploaded on
+ * any other stream before this call are complete; with a caller's stream the caller orders its
+ * uploads before the first step (same stream, or an event). */
 int kllm_decoder_create(const kllm_decoder_desc* desc, void* stream, kllm_decoder** out);
 void kllm_decoder_destroy(kllm_decoder* dec);
 

@@ -319,6 +319,13 @@ int kllm_decoder_create(const kllm_decoder_desc* desc, void* stream, kllm_decode
       return KLLM_E_NODEVICE;
     }
     dc->own_stream = true;
+    // A private non-blocking stream does not order against the legacy default stream: weights the
+    // caller uploaded or produced there (or anywhere else) must have landed before the first launch.
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+      cudaStreamDestroy(dc->stream);
+      delete dc;
+      return KLLM_E_NODEVICE;
+    }
   }
 
   auto fail = [&](int rc) {
@@ -368,6 +375,7 @@ int kllm_decoder_create(const kllm_decoder_desc* desc, void* stream, kllm_decode
   if (!force_graph && mega_ok) {
     MegaModel mm{};
     mm.tp_world = tp, mm.tp_rank = tp_rank, mm.tp_stride = tp_stride;
+    mm.numerics = d.numerics;
     for (int r = 0; r < 8; ++r) mm.tp_data[r] = tp_areas[r];
     mm.dim = d.dim, mm.hidden_dim = d.hidden_dim, mm.layer_num = L, mm.head_num = d.head_num;
     mm.kv_head_num = d.kv_head_num, mm.vocab_size = d.vocab_size, mm.seq_len = d.seq_len;
@@ -506,7 +514,7 @@ int kllm_decoder_prefill_tf32(kllm_decoder* dc, const int32_t* tokens_host, int3
   m.dim = d.dim, m.hidden_dim = d.hidden_dim, m.layer_num = d.layer_num, m.head_num = d.head_num;
   m.kv_head_num = d.kv_head_num, m.vocab_size = d.vocab_size, m.seq_len = d.seq_len, m.head_size = hs;
   m.flavour = d.flavour, m.mega_layout = dc->use_mega ? 1 : 0, m.eps = flavour_eps(d.flavour);
-  m.attn_split = dc->use_mega ? dc->mega.attn_split() : 1;
+  m.attn_split = dc->use_mega ? dc->mega.attn_vsplit() : 1;
   m.tok_emb = d.tok_emb, m.attn_norm = dc->attn_norm.data(), m.ffn_norm = dc->ffn_norm.data();
   m.wq = dc->wq.data(), m.wk = dc->wk.data(), m.wv = dc->wv.data(), m.wo = dc->wo.data();
   m.w1 = dc->w1.data(), m.w2 = dc->w2.data(), m.w3 = dc->w3.data();
@@ -631,7 +639,7 @@ int kllm_decoder_read_kv(kllm_decoder* dc, float* key_host, float* value_host) {
   KLLM_TRY(cudaMemcpy(kraw.data(), dc->kcache, n * sizeof(float), cudaMemcpyDeviceToHost));
   KLLM_TRY(cudaMemcpy(vraw.data(), dc->vcache, n * sizeof(float), cudaMemcpyDeviceToHost));
   const size_t nh = kvd / hs;
-  const size_t SP = static_cast<size_t>(dc->mega.attn_split()), dv = hs / SP;
+  const size_t SP = static_cast<size_t>(dc->mega.attn_vsplit()), dv = hs / SP;
   for (size_t l = 0; l < L; ++l)
     for (size_t g = 0; g < nh; ++g) {
       const float* kb = kraw.data() + (l * nh + g) * S * hs;

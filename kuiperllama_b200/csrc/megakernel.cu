@@ -59,6 +59,11 @@ namespace mega {
 #ifndef KLLM_MBAR_HINT_NS
 #define KLLM_MBAR_HINT_NS 20000u
 #endif
+// 1: warps without a row in an attention tile skip its wait and block at a hardware barrier instead of
+// spinning on the mbarrier.  Measured on B200 (profiles/README.md, pass M): no gain (826 vs 837 tok/s), so off.
+#ifndef KLLM_ATTN_GATE
+#define KLLM_ATTN_GATE 0
+#endif
 #ifndef KLLM_TASK_ROWS
 #define KLLM_TASK_ROWS 4
 #endif
@@ -146,6 +151,10 @@ __device__ __forceinline__ void ld_tagged2(const unsigned long long* p, unsigned
 // local (same GPU) flavour of the tagged words
 __device__ __forceinline__ void st_tagged_gpu(unsigned long long* p, float v, unsigned tag) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(tagged_word(v, tag)) : "memory");
+}
+__device__ __forceinline__ void st_tagged2_gpu(unsigned long long* p, float v0, float v1, unsigned tag) {  // 16-byte aligned
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(tagged_word(v0, tag)), "l"(tagged_word(v1, tag))
+               : "memory");
 }
 __device__ __forceinline__ unsigned long long ld_tagged_gpu(const unsigned long long* p) {
   unsigned long long w;
@@ -651,13 +660,283 @@ __device__ KLLM_STAGE_CALL void stage_handoff(const unsigned long long* src, uns
 //       block and "thread i walks column i" is conflict-free.
 // Rows t < pos were written by earlier tokens, so -- like weights -- the producer warp streams
 // them through the ring ahead of time; only row pos is handled here from registers.
+constexpr bool kAttnGate = KLLM_ATTN_GATE != 0;
 __device__ __forceinline__ int attn_tiles(int pos, int T) { return (pos + T - 1) / T; }
 // tiles j = s, s + SP, ... < n
 __device__ __forceinline__ int own_tiles(int n, int s, int SP) { return n > s ? (n - s + SP - 1) / SP : 0; }
 
+// One output element's P.V chain over nt timesteps of a staged tile: value += pr[tt] * vt[tt * stride],
+// strictly left to right (mha_kernel.cu:97-109).  The chain is latency bound (one dependent FFMA per
+// step), so the operands of the next eight steps are loaded while the current eight retire.
+// pv_chain_smem: probabilities in shared memory (the usual case) -- explicit ld.shared, the eight
+// probabilities of a batch as two 128-bit loads (pr_addr is 16-byte aligned: tiles start at
+// multiples of 32 timesteps).  pv_chain: probabilities behind a generic pointer (global fallback).
+__device__ __forceinline__ float pv_chain_smem(uint32_t pr_addr, uint32_t vt_addr, int stride_bytes, int nt, float value) {
+  // two register sets (A: steps tt .. tt+7, B: tt+8 .. tt+15) loaded alternately, so the loop carries no
+  // register moves and every load has a whole 8-step chain (>= 32 cycles) to land
+  auto load8 = [&](int t, float4& p0, float4& p1, float (&v)[8]) {
+    p0 = lds_f4(pr_addr + t * 4), p1 = lds_f4(pr_addr + t * 4 + 16);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = lds_f32(vt_addr + (t + k) * stride_bytes);
+  };
+  auto chain8 = [&](const float4& p0, const float4& p1, const float (&v)[8]) {
+    value = __fmaf_rn(p0.x, v[0], value);
+    value = __fmaf_rn(p0.y, v[1], value);
+    value = __fmaf_rn(p0.z, v[2], value);
+    value = __fmaf_rn(p0.w, v[3], value);
+    value = __fmaf_rn(p1.x, v[4], value);
+    value = __fmaf_rn(p1.y, v[5], value);
+    value = __fmaf_rn(p1.z, v[6], value);
+    value = __fmaf_rn(p1.w, v[7], value);
+  };
+  int tt = 0;
+  if (nt >= 8) {
+    float4 a0, a1, b0, b1;
+    float va[8], vb[8];
+    load8(0, a0, a1, va);
+    for (; tt + 24 <= nt; tt += 16) {  // A holds tt .. tt+7
+      load8(tt + 8, b0, b1, vb);
+      chain8(a0, a1, va);
+      load8(tt + 16, a0, a1, va);
+      chain8(b0, b1, vb);
+    }
+    if (tt + 16 <= nt) {
+      load8(tt + 8, b0, b1, vb);
+      chain8(a0, a1, va);
+      chain8(b0, b1, vb);
+      tt += 16;
+    } else {
+      chain8(a0, a1, va);
+      tt += 8;
+    }
+  }
+  for (; tt < nt; ++tt) value = __fmaf_rn(lds_f32(pr_addr + tt * 4), lds_f32(vt_addr + tt * stride_bytes), value);
+  return value;
+}
+__device__ __forceinline__ float pv_chain(const float* pr, const float* vt, int stride, int nt, float value) {
+#pragma unroll 8
+  for (int tt = 0; tt < nt; ++tt) value = __fmaf_rn(pr[tt], vt[tt * stride], value);
+  return value;
+}
+
+// Fused form (attn_split == 1, one CTA per head does scores, softmax and P.V in ONE phase): one
+// hand-off less per layer, the better trade when a head's K and V are small (head_size 64).
+template <int CW>
+__device__ KLLM_PHASE_CALL Pipe attention_fused_phase(const Params& P, int head, int pos, Pipe pipe, unsigned tag_in,
+                                                 unsigned tag_out, unsigned long long* stamp) {
+  const Phase& ph = g_ph_cons;
+  float* ws = reinterpret_cast<float*>(smem);
+  float* s_warp = g_s_warp;
+  float* s_bcast = &g_s_bcast;
+  unsigned char* stages = smem + P.xbuf_bytes + P.xres_bytes;
+  uint64_t* full_bar = g_full_bar;
+  uint64_t* empty_bar = g_empty_bar;
+  constexpr int CT = CW * 32;
+  const int tid = threadIdx.x;
+  const long long c_begin = stamp ? clock64() : 0;
+  long long c_wait = 0;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int hs = P.head_size, seq_len = P.seq_len, T = P.attn_tile, S = P.num_stages;
+  float* q_s = ws;       // [hs] rotated query
+  float* k_s = ws + hs;  // [hs] rotated key of the current position
+  const int kvh = head / P.kv_mul;
+  const size_t head_block = (static_cast<size_t>(ph.layer) * (P.kv_dim / hs) + kvh) * seq_len * hs;
+  float* kcache = P.key_cache + head_block;
+  const float* vcache = P.value_cache + head_block;
+  // scores / probabilities: shared memory when the context fits the workspace (the ring leaves
+  // almost no L1), else the global [head][seq_len] buffer the reference uses
+  const int smem_cap = (P.xbuf_bytes >> 2) - 2 * hs;
+  const bool score_in_smem = pos + 1 <= smem_cap;
+  float* score_head = score_in_smem ? (ws + 2 * hs) : (P.score + static_cast<size_t>(head) * seq_len);
+
+  // value row of the current position (written by the QKV phase of this token)
+  const bool handoff = ph.tq != nullptr;  // q / k / v arrive as tagged words: no barrier before us
+  float v_pos = 0.f;
+  if (tid < hs)
+    v_pos = handoff ? poll_tagged(ph.tv + kvh * hs + tid, tag_in) : __ldcg(vcache + static_cast<size_t>(pos) * hs + tid);
+
+  // RoPE on q (this head) and on the new key row, rope_kernel.cu as compiled (elementwise.cu)
+  if (tid < hs / 2) {
+    const float* qg = P.q + static_cast<size_t>(head) * hs;
+    const float* kg = P.k_raw + kvh * hs;
+    int i0, i1;
+    if (P.flavour == KLLM_FLAVOUR_LLAMA2) {
+      i0 = 2 * tid, i1 = 2 * tid + 1;
+    } else {
+      i0 = tid, i1 = tid + hs / 2;
+    }
+    const int ci = 2 * tid;
+    const float fci = P.sin_cache[static_cast<size_t>(pos) * hs + ci];
+    const float fcr = P.cos_cache[static_cast<size_t>(pos) * hs + ci];
+    const float q0 = handoff ? poll_tagged(ph.tq + head * hs + i0, tag_in) : __ldcg(qg + i0);
+    const float q1 = handoff ? poll_tagged(ph.tq + head * hs + i1, tag_in) : __ldcg(qg + i1);
+    q_s[i0] = __fmaf_rn(fcr, q0, -__fmul_rn(fci, q1));
+    q_s[i1] = __fmaf_rn(fci, q0, __fmul_rn(fcr, q1));
+    const float k0 = handoff ? poll_tagged(ph.tk + kvh * hs + i0, tag_in) : __ldcg(kg + i0);
+    const float k1 = handoff ? poll_tagged(ph.tk + kvh * hs + i1, tag_in) : __ldcg(kg + i1);
+    const float r0 = __fmaf_rn(fcr, k0, -__fmul_rn(fci, k1));
+    const float r1 = __fmaf_rn(fci, k0, __fmul_rn(fcr, k1));
+    k_s[i0] = r0;
+    k_s[i1] = r1;
+    if (head % P.kv_mul == 0) {  // one writer per kv head stores the rotated key
+      kcache[(static_cast<size_t>(i0 >> 2) * seq_len + pos) * 4 + (i0 & 3)] = r0;
+      kcache[(static_cast<size_t>(i1 >> 2) * seq_len + pos) * 4 + (i1 & 3)] = r1;
+    }
+  }
+  consumer_sync<CT>();
+  const long long c_rope = stamp ? clock64() : 0;
+
+  // ---- scores: one left-to-right FFMA chain per timestep (mha_kernel.cu:61-91) ---------------
+  const float scale = 1.f / sqrtf(static_cast<float>(hs));
+  const float4* q4 = reinterpret_cast<const float4*>(q_s);
+  const int n_tiles = attn_tiles(pos, T);
+  for (int j = 0; j < n_tiles; ++j) {
+    const int t0 = j * T;
+    const int nt = min(T, pos - t0);
+    // warps without a row in this tile do not wait for it (a spinning warp costs its neighbours
+    // issue slots and shared-memory queue entries): they arrive at once and block at the hardware
+    // barrier below, which also keeps them from lapping the ring
+    const bool works = !kAttnGate || ((tid & ~31) < nt);
+    if (works) {
+      const long long w0 = stamp ? clock64() : 0;
+      mbar_wait(&full_bar[pipe.slot], pipe.parity);
+      if (stamp) c_wait += clock64() - w0;
+    }
+    const float4* tile = reinterpret_cast<const float4*>(stages + static_cast<size_t>(pipe.slot) * P.stage_bytes);
+    if (tid < nt) {
+      float score = 0.0f;
+#pragma unroll 4
+      for (int c = 0; c < (hs >> 2); ++c) {
+        const float4 kv = tile[c * T + tid];
+        const float4 qv = q4[c];
+        score = __fmaf_rn(kv.x, qv.x, score);
+        score = __fmaf_rn(kv.y, qv.y, score);
+        score = __fmaf_rn(kv.z, qv.z, score);
+        score = __fmaf_rn(kv.w, qv.w, score);
+      }
+      score_head[t0 + tid] = __fmul_rn(score, scale);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
+    pipe.advance(S);
+    if (kAttnGate) consumer_sync<CT>();
+  }
+  if (tid == 0) {  // t == pos from the freshly rotated key
+    const float4* k4 = reinterpret_cast<const float4*>(k_s);
+    float score = 0.0f;
+    for (int c = 0; c < (hs >> 2); ++c) {
+      const float4 kv = k4[c];
+      const float4 qv = q4[c];
+      score = __fmaf_rn(kv.x, qv.x, score);
+      score = __fmaf_rn(kv.y, qv.y, score);
+      score = __fmaf_rn(kv.z, qv.z, score);
+      score = __fmaf_rn(kv.w, qv.w, score);
+    }
+    score_head[pos] = __fmul_rn(score, scale);
+  }
+  consumer_sync<CT>();
+  const long long c_scores = stamp ? clock64() : 0;
+  const long long c_wait_scores = c_wait;
+
+  // ---- softmax, mha_kernel.cu:7-45: the reference runs 256 strided threads and cub<256> block
+  // reductions.  Here 128 threads play two virtual threads each (v = tid and v = tid + 128, i.e.
+  // elements tid + 256 k and tid + 128 + 256 k): the maximum does not care about order, and for the
+  // sum each virtual thread keeps its own left-to-right partial, each virtual warp its own shuffle
+  // tree (real warp q holds virtual warps q and q + 4), then the eight warp sums are added in order.
+  const int size = pos + 1;
+  constexpr int kHalf = kSoftmaxThreads / 2;  // 128 real threads
+  static_assert(CT >= kHalf, "softmax needs 128 consumer threads");
+  const bool sm_thread = tid < kHalf;
+  float max_val = -FLT_MAX;
+  if (sm_thread)
+    for (int i = tid; i < size; i += kHalf) max_val = fmaxf(max_val, score_head[i]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) max_val = fmaxf(max_val, __shfl_xor_sync(kFull, max_val, off));
+  if (lane == 0 && sm_thread) s_warp[warp] = max_val;
+  consumer_sync<CT>();
+  max_val = fmaxf(fmaxf(s_warp[0], s_warp[1]), fmaxf(s_warp[2], s_warp[3]));
+  consumer_sync<CT>();
+
+  float sum_lo = 0.0f, sum_hi = 0.0f;  // virtual threads tid and tid + 128
+  if (sm_thread) {
+    for (int i = tid; i < size; i += kSoftmaxThreads) {
+      const float e = expf(score_head[i] - max_val);
+      score_head[i] = e;
+      sum_lo += e;
+    }
+    for (int i = tid + kHalf; i < size; i += kSoftmaxThreads) {
+      const float e = expf(score_head[i] - max_val);
+      score_head[i] = e;
+      sum_hi += e;
+    }
+  }
+  sum_lo = warp_tree_sum(sum_lo);
+  sum_hi = warp_tree_sum(sum_hi);
+  if (lane == 0 && sm_thread) {
+    s_warp[warp] = sum_lo;      // virtual warp `warp`
+    s_warp[warp + 4] = sum_hi;  // virtual warp `warp + 4`
+  }
+  consumer_sync<CT>();
+  if (tid == 0) {
+    float total = s_warp[0];
+#pragma unroll
+    for (int w = 1; w < kSoftmaxThreads / 32; ++w) total = __fadd_rn(total, s_warp[w]);
+    *s_bcast = total;
+  }
+  consumer_sync<CT>();
+  const float sum = *s_bcast;
+  for (int i = tid; i < size; i += CT) score_head[i] = score_head[i] / sum;
+  consumer_sync<CT>();
+  const long long c_soft = stamp ? clock64() : 0;
+
+  // ---- weighted value sum, mha_kernel.cu:97-109: one FFMA chain per output element ----------------
+  float value = 0.0f;
+  const int Tv = P.attn_tile_v, n_tiles_v = attn_tiles(pos, Tv);
+  for (int j = 0; j < n_tiles_v; ++j) {
+    const int t0 = j * Tv;
+    const int nt = min(Tv, pos - t0);
+    // warps without a row in this tile do not wait for it (a spinning warp costs its neighbours
+    // issue slots and shared-memory queue entries): they arrive at once and block at the hardware
+    // barrier below, which also keeps them from lapping the ring
+    const bool works = !kAttnGate || ((tid & ~31) < hs);
+    if (works) {
+      const long long w0 = stamp ? clock64() : 0;
+      mbar_wait(&full_bar[pipe.slot], pipe.parity);
+      if (stamp) c_wait += clock64() - w0;
+    }
+    if (tid < hs) {
+      const float* vt = reinterpret_cast<const float*>(stages + static_cast<size_t>(pipe.slot) * P.stage_bytes) + tid;
+      value = score_in_smem ? pv_chain_smem(smem_u32(score_head + t0), smem_u32(vt), hs * 4, nt, value)
+                            : pv_chain(score_head + t0, vt, hs, nt, value);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
+    pipe.advance(S);
+    if (kAttnGate) consumer_sync<CT>();
+  }
+  if (tid < hs) {
+    value = __fmaf_rn(score_head[pos], v_pos, value);
+    if (ph.ta != nullptr)
+      st_tagged_gpu(ph.ta + static_cast<size_t>(head) * hs + tid, value, tag_out);
+    else
+      P.attn_out[static_cast<size_t>(head) * hs + tid] = value;
+  }
+  if (stamp && tid == 0) {  // SM cycles of thread 0 (profiles/: tools/phase_timeline.py)
+    const long long c_end = clock64();
+    stamp[4] = static_cast<unsigned long long>(c_rope - c_begin);                             // q/k/v poll + RoPE
+    stamp[5] = static_cast<unsigned long long>(c_scores - c_rope - c_wait_scores);            // scores
+    stamp[6] = static_cast<unsigned long long>(c_soft - c_scores);                            // softmax
+    stamp[7] = static_cast<unsigned long long>(c_end - c_soft - (c_wait - c_wait_scores));    // P.V
+    stamp[8] = static_cast<unsigned long long>(c_wait);                                       // ring waits
+    stamp[9] = static_cast<unsigned long long>(c_wait - c_wait_scores);                       // of which V tiles
+  }
+  return pipe;
+}
+
+
 template <int CW>
 __device__ KLLM_PHASE_CALL Pipe attention_scores_phase(const Params& P, int head, int split, int pos, Pipe pipe,
-                                                        unsigned tag_in, unsigned tag_out) {
+                                                        unsigned tag_in, unsigned tag_out, unsigned long long* stamp) {
   const Phase& ph = g_ph_cons;
   float* ws = reinterpret_cast<float*>(smem);
   unsigned char* stages = smem + P.xbuf_bytes + P.xres_bytes;
@@ -665,6 +944,8 @@ __device__ KLLM_PHASE_CALL Pipe attention_scores_phase(const Params& P, int head
   uint64_t* empty_bar = g_empty_bar;
   constexpr int CT = CW * 32;
   const int tid = threadIdx.x;
+  const long long c_begin = stamp ? clock64() : 0;
+  long long c_wait = 0;
   const int lane = tid & 31;
   const int hs = P.head_size, seq_len = P.seq_len, T = P.attn_tile, S = P.num_stages, SP = P.attn_split;
   float* q_s = ws;       // [hs] rotated query
@@ -706,6 +987,7 @@ __device__ KLLM_PHASE_CALL Pipe attention_scores_phase(const Params& P, int head
     }
   }
   consumer_sync<CT>();
+  const long long c_rope = stamp ? clock64() : 0;
 
   // ---- scores: one left-to-right FFMA chain per timestep (mha_kernel.cu:61-91) ---------------
   const float scale = 1.f / sqrtf(static_cast<float>(hs));
@@ -714,7 +996,15 @@ __device__ KLLM_PHASE_CALL Pipe attention_scores_phase(const Params& P, int head
   for (int j = split; j < n_tiles; j += SP) {
     const int t0 = j * T;
     const int nt = min(T, pos - t0);
-    mbar_wait(&full_bar[pipe.slot], pipe.parity);
+    // warps without a row in this tile do not wait for it (a spinning warp costs its neighbours
+    // issue slots and shared-memory queue entries): they arrive at once and block at the hardware
+    // barrier below, which also keeps them from lapping the ring
+    const bool works = !kAttnGate || ((tid & ~31) < nt);
+    if (works) {
+      const long long w0 = stamp ? clock64() : 0;
+      mbar_wait(&full_bar[pipe.slot], pipe.parity);
+      if (stamp) c_wait += clock64() - w0;
+    }
     const float4* tile = reinterpret_cast<const float4*>(stages + static_cast<size_t>(pipe.slot) * P.stage_bytes);
     if (tid < nt) {
       float score = 0.0f;
@@ -732,6 +1022,7 @@ __device__ KLLM_PHASE_CALL Pipe attention_scores_phase(const Params& P, int head
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
     pipe.advance(S);
+    if (kAttnGate) consumer_sync<CT>();
   }
   if (split == 0 && tid == 0) {  // t == pos from the freshly rotated key
     const float4* k4 = reinterpret_cast<const float4*>(k_s);
@@ -746,12 +1037,19 @@ __device__ KLLM_PHASE_CALL Pipe attention_scores_phase(const Params& P, int head
     }
     st_tagged_gpu(sc_out + pos, __fmul_rn(score, scale), tag_out);
   }
+  if (stamp && tid == 0) {
+    const long long c_end = clock64();
+    stamp[4] = static_cast<unsigned long long>(c_rope - c_begin);           // q/k poll + RoPE
+    stamp[5] = static_cast<unsigned long long>(c_end - c_rope - c_wait);    // scores
+    stamp[8] = static_cast<unsigned long long>(c_wait);                     // ring waits (K tiles)
+  }
   return pipe;
 }
 
 template <int CW>
 __device__ KLLM_PHASE_CALL Pipe attention_pv_phase(const Params& P, int head, int split, int pos, Pipe pipe,
-                                                   unsigned tag_scores, unsigned tag_qkv, unsigned tag_out) {
+                                                   unsigned tag_scores, unsigned tag_qkv, unsigned tag_out,
+                                                   unsigned long long* stamp) {
   const Phase& ph = g_ph_cons;
   float* ws = reinterpret_cast<float*>(smem);
   float* s_warp = g_s_warp;
@@ -761,6 +1059,8 @@ __device__ KLLM_PHASE_CALL Pipe attention_pv_phase(const Params& P, int head, in
   uint64_t* empty_bar = g_empty_bar;
   constexpr int CT = CW * 32;
   const int tid = threadIdx.x;
+  const long long c_begin = stamp ? clock64() : 0;
+  long long c_wait = 0;
   const int lane = tid & 31, warp = tid >> 5;
   const int hs = P.head_size, seq_len = P.seq_len, S = P.num_stages, SP = P.attn_split;
   const int dv = hs / SP, T = P.attn_tile_v;
@@ -773,7 +1073,8 @@ __device__ KLLM_PHASE_CALL Pipe attention_pv_phase(const Params& P, int head, in
   // almost no L1), else the global [head][seq_len] buffer the reference uses (the SP CTAs of a head
   // then write identical values to it)
   const int smem_cap = P.xbuf_bytes >> 2;
-  float* score_head = (pos + 1 <= smem_cap) ? ws : (P.score + static_cast<size_t>(head) * seq_len);
+  const bool score_in_smem = pos + 1 <= smem_cap;
+  float* score_head = score_in_smem ? ws : (P.score + static_cast<size_t>(head) * seq_len);
 
   // this CTA's dv dims of the value row of the current position (written by the QKV phase of this token)
   float v_pos = 0.f;
@@ -791,6 +1092,7 @@ __device__ KLLM_PHASE_CALL Pipe attention_pv_phase(const Params& P, int head, in
     if (tid < 4 && rest < size) score_head[rest] = poll_tagged(sc_in + rest, tag_scores);
   }
   consumer_sync<CT>();
+  const long long c_poll = stamp ? clock64() : 0;
 
   // ---- softmax, mha_kernel.cu:7-45: the reference runs 256 strided threads and cub<256> block
   // reductions.  Here 128 threads play two virtual threads each (v = tid and v = tid + 128, i.e.
@@ -840,6 +1142,7 @@ __device__ KLLM_PHASE_CALL Pipe attention_pv_phase(const Params& P, int head, in
   const float sum = *s_bcast;
   for (int i = tid; i < size; i += CT) score_head[i] = score_head[i] / sum;
   consumer_sync<CT>();
+  const long long c_soft = stamp ? clock64() : 0;
 
   // ---- weighted value sum, mha_kernel.cu:97-109: one FFMA chain per output element ----------------
   float value = 0.0f;
@@ -847,16 +1150,24 @@ __device__ KLLM_PHASE_CALL Pipe attention_pv_phase(const Params& P, int head, in
   for (int j = 0; j < n_tiles; ++j) {
     const int t0 = j * T;
     const int nt = min(T, pos - t0);
-    mbar_wait(&full_bar[pipe.slot], pipe.parity);
+    // warps without a row in this tile do not wait for it (a spinning warp costs its neighbours
+    // issue slots and shared-memory queue entries): they arrive at once and block at the hardware
+    // barrier below, which also keeps them from lapping the ring
+    const bool works = !kAttnGate || ((tid & ~31) < dv);
+    if (works) {
+      const long long w0 = stamp ? clock64() : 0;
+      mbar_wait(&full_bar[pipe.slot], pipe.parity);
+      if (stamp) c_wait += clock64() - w0;
+    }
     if (tid < dv) {
       const float* vt = reinterpret_cast<const float*>(stages + static_cast<size_t>(pipe.slot) * P.stage_bytes) + tid;
-      const float* pr = score_head + t0;
-#pragma unroll 8
-      for (int tt = 0; tt < nt; ++tt) value = __fmaf_rn(pr[tt], vt[tt * dv], value);
+      value = score_in_smem ? pv_chain_smem(smem_u32(score_head + t0), smem_u32(vt), dv * 4, nt, value)
+                            : pv_chain(score_head + t0, vt, dv, nt, value);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
     pipe.advance(S);
+    if (kAttnGate) consumer_sync<CT>();
   }
   if (tid < dv) {
     value = __fmaf_rn(score_head[pos], v_pos, value);
@@ -865,6 +1176,247 @@ __device__ KLLM_PHASE_CALL Pipe attention_pv_phase(const Params& P, int head, in
       st_tagged_gpu(ph.ta + static_cast<size_t>(head) * hs + d, value, tag_out);
     else
       P.attn_out[static_cast<size_t>(head) * hs + d] = value;
+  }
+  if (stamp && tid == 0) {
+    const long long c_end = clock64();
+    stamp[4] = static_cast<unsigned long long>(c_poll - c_begin);           // scores (+ v row) polled
+    stamp[6] = static_cast<unsigned long long>(c_soft - c_poll);            // softmax
+    stamp[7] = static_cast<unsigned long long>(c_end - c_soft - c_wait);    // P.V
+    stamp[8] = static_cast<unsigned long long>(c_wait);                     // ring waits (V tiles)
+  }
+  return pipe;
+}
+
+// Toleranced attention (numerics "fast"): flash-decoding.  With the summation order free, a head is
+// split over SP CTAs BY TIMESTEP -- CTA (head, s) takes the tiles j = s, s + SP, ... of T timesteps, K
+// and V -- and inside the CTA every WARP runs its own online softmax over blocks of 8 timesteps
+// (blocks dealt round-robin to the warps), so a tile costs no block-wide barrier at all:
+//   scores   lane (cg, tt) = (lane / 8, lane % 8) dots timestep tt of the block with a quarter of
+//            head_size (conflict-free 128-bit reads of the K tile [hs/4][T][4]); two xor-shuffles sum
+//            the quarters, three more give the block's maximum and sum -> running (m, l) of the warp;
+//   P.V      lane owns output dims lane, lane + 32, ...: o[d] = o[d] alpha + sum_tt p_tt v[tt][d] with p_tt
+//            shuffled from lane tt (conflict-free 32-bit reads of the V tile [T][hs]).
+// At the end the CW warp partials (m, l, o[hs]) are merged through shared memory, CTA 0 of the head folds
+// in the current position's row from registers and merges the partials of the other CTAs that had
+// tiles (tagged words in the scores area: [head][s][hs + 2]); at short contexts (pos <= T) that is
+// nobody, and the phase costs what the fused one does.
+template <int CW>
+__device__ KLLM_PHASE_CALL Pipe attention_flash_phase(const Params& P, int head, int split, int pos, Pipe pipe,
+                                                       unsigned tag_in, unsigned tag_out, unsigned long long* stamp) {
+  const Phase& ph = g_ph_cons;
+  float* ws = reinterpret_cast<float*>(smem);
+  unsigned char* stages = smem + P.xbuf_bytes + P.xres_bytes;
+  uint64_t* full_bar = g_full_bar;
+  uint64_t* empty_bar = g_empty_bar;
+  constexpr int CT = CW * 32;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const long long c_begin = stamp ? clock64() : 0;
+  long long c_wait = 0, c_sc = 0, c_pv = 0;
+  const int hs = P.head_size, seq_len = P.seq_len, T = P.attn_tile, S = P.num_stages, SP = P.attn_split;
+  const int n_tiles = attn_tiles(pos, T);
+  // CTAs without a tile have nothing to say (their partial would weigh zero): only CTA 0 always runs
+  if (split != 0 && split >= n_tiles) return pipe;
+  float* q_s = ws;                // [hs] rotated query
+  float* k_s = ws + hs;           // [hs] rotated key of the current position
+  float* red = ws + 2 * hs;       // [CW][hs + 2] warp partials: m, l, o[hs]
+  const int kvh = head / P.kv_mul;
+  const size_t head_block = (static_cast<size_t>(ph.layer) * (P.kv_dim / hs) + kvh) * seq_len * hs;
+  float* kcache = P.key_cache + head_block;
+  const bool handoff = ph.tq != nullptr;  // q / k / v arrive as tagged words: no barrier before us
+
+  float v_pos = 0.f;  // the value row of the current position (CTA 0 of the head)
+  if (split == 0 && tid < hs)
+    v_pos = handoff ? poll_tagged(ph.tv + kvh * hs + tid, tag_in)
+                    : __ldcg(P.value_cache + head_block + static_cast<size_t>(pos) * hs + tid);
+  if (tid < hs / 2) {  // RoPE on q (this head) and on the new key row (rope_kernel.cu as compiled)
+    const float* qg = P.q + static_cast<size_t>(head) * hs;
+    const float* kg = P.k_raw + kvh * hs;
+    int i0, i1;
+    if (P.flavour == KLLM_FLAVOUR_LLAMA2) {
+      i0 = 2 * tid, i1 = 2 * tid + 1;
+    } else {
+      i0 = tid, i1 = tid + hs / 2;
+    }
+    const int ci = 2 * tid;
+    const float fci = P.sin_cache[static_cast<size_t>(pos) * hs + ci];
+    const float fcr = P.cos_cache[static_cast<size_t>(pos) * hs + ci];
+    const float q0 = handoff ? poll_tagged(ph.tq + head * hs + i0, tag_in) : __ldcg(qg + i0);
+    const float q1 = handoff ? poll_tagged(ph.tq + head * hs + i1, tag_in) : __ldcg(qg + i1);
+    q_s[i0] = __fmaf_rn(fcr, q0, -__fmul_rn(fci, q1));
+    q_s[i1] = __fmaf_rn(fci, q0, __fmul_rn(fcr, q1));
+    if (split == 0) {
+      const float k0 = handoff ? poll_tagged(ph.tk + kvh * hs + i0, tag_in) : __ldcg(kg + i0);
+      const float k1 = handoff ? poll_tagged(ph.tk + kvh * hs + i1, tag_in) : __ldcg(kg + i1);
+      const float r0 = __fmaf_rn(fcr, k0, -__fmul_rn(fci, k1));
+      const float r1 = __fmaf_rn(fci, k0, __fmul_rn(fcr, k1));
+      k_s[i0] = r0;
+      k_s[i1] = r1;
+      if (head % P.kv_mul == 0) {  // one writer per kv head stores the rotated key
+        kcache[(static_cast<size_t>(i0 >> 2) * seq_len + pos) * 4 + (i0 & 3)] = r0;
+        kcache[(static_cast<size_t>(i1 >> 2) * seq_len + pos) * 4 + (i1 & 3)] = r1;
+      }
+    }
+  }
+  consumer_sync<CT>();
+  const long long c_rope = stamp ? clock64() : 0;
+
+  const float scale = 1.f / sqrtf(static_cast<float>(hs));
+  const float4* q4 = reinterpret_cast<const float4*>(q_s);
+  const int cg = lane >> 3, tt = lane & 7;
+  const int cpg = hs >> 4;        // 16-byte chunks per quarter of head_size (host: head_size % 16 == 0)
+  float m = -FLT_MAX, l = 0.f;
+  float o[4] = {0.f, 0.f, 0.f, 0.f};  // output dims lane, lane + 32, lane + 64, lane + 96 (< hs)
+  int blk0 = 0;                   // blocks dealt so far: block b of the CTA goes to warp b % CW
+  for (int j = split; j < n_tiles; j += SP) {
+    const int t0 = j * T;
+    const int nt = min(T, pos - t0);
+    const long long w0 = stamp ? clock64() : 0;
+    mbar_wait(&full_bar[pipe.slot], pipe.parity);  // K tile
+    const uint32_t ktile = smem_u32(stages + static_cast<size_t>(pipe.slot) * P.stage_bytes);
+    const int kslot = pipe.slot;
+    pipe.advance(S);
+    mbar_wait(&full_bar[pipe.slot], pipe.parity);  // V tile
+    const uint32_t vtile = smem_u32(stages + static_cast<size_t>(pipe.slot) * P.stage_bytes);
+    const long long w1 = stamp ? clock64() : 0;
+    c_wait += w1 - w0;
+    const int nb = (nt + 7) >> 3;
+    for (int b = (warp - blk0 % CW + CW) % CW; b < nb; b += CW) {
+      const long long s0 = stamp ? clock64() : 0;
+      const int tl = b * 8 + tt;  // this lane's timestep within the tile
+      const bool valid = tl < nt;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      if (valid) {
+#pragma unroll 4
+        for (int c = cg * cpg; c < (cg + 1) * cpg; ++c) {
+          const float4 kv = lds_f4(ktile + static_cast<uint32_t>(c * T + tl) * 16u);
+          const float4 qv = q4[c];
+          a0 = __fmaf_rn(kv.x, qv.x, a0);
+          a1 = __fmaf_rn(kv.y, qv.y, a1);
+          a2 = __fmaf_rn(kv.z, qv.z, a2);
+          a3 = __fmaf_rn(kv.w, qv.w, a3);
+        }
+      }
+      float sc = (a0 + a1) + (a2 + a3);
+      sc += __shfl_xor_sync(kFull, sc, 8);
+      sc += __shfl_xor_sync(kFull, sc, 16);
+      sc = valid ? sc * scale : -FLT_MAX;
+      float mb = sc;
+      mb = fmaxf(mb, __shfl_xor_sync(kFull, mb, 1));
+      mb = fmaxf(mb, __shfl_xor_sync(kFull, mb, 2));
+      mb = fmaxf(mb, __shfl_xor_sync(kFull, mb, 4));
+      const float m_new = fmaxf(m, mb);
+      const float alpha = expf(m - m_new);
+      const float pr = valid ? expf(sc - m_new) : 0.f;
+      float ps = pr;
+      ps += __shfl_xor_sync(kFull, ps, 1);
+      ps += __shfl_xor_sync(kFull, ps, 2);
+      ps += __shfl_xor_sync(kFull, ps, 4);
+      l = __fmaf_rn(l, alpha, ps);
+      m = m_new;
+      const long long s1 = stamp ? clock64() : 0;
+      c_sc += s1 - s0;
+      // P.V of the block
+      const int nv = min(8, nt - b * 8);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t vrow = vtile + static_cast<uint32_t>(b * 8 * hs + lane) * 4u;
+      for (int k = 0; k < nv; ++k) {
+        const float pk = __shfl_sync(kFull, pr, k);
+        const uint32_t va = vrow + static_cast<uint32_t>(k * hs) * 4u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (lane + 32 * i < hs) acc[i] = __fmaf_rn(pk, lds_f32(va + 128u * i), acc[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = __fmaf_rn(o[i], alpha, acc[i]);
+      if (stamp) c_pv += clock64() - s1;
+    }
+    blk0 += nb;
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&empty_bar[kslot]);
+      mbar_arrive(&empty_bar[pipe.slot]);
+    }
+    pipe.advance(S);
+  }
+  const long long c_tiles = stamp ? clock64() : 0;
+  // ---- merge the warps' partials: thread d < hs ends with the CTA's (m, l, o[d]) ---------------------
+  {
+    float* mine = red + warp * (hs + 2);
+    if (lane == 0) mine[0] = m, mine[1] = l;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (lane + 32 * i < hs) mine[2 + lane + 32 * i] = o[i];
+  }
+  consumer_sync<CT>();
+  if (tid < hs) {
+    float M = red[0];
+    for (int w = 1; w < CW; ++w) M = fmaxf(M, red[w * (hs + 2)]);
+    float num = 0.f, den = 0.f;
+    for (int w = 0; w < CW; ++w) {
+      const float* theirs = red + w * (hs + 2);
+      const float wgt = expf(theirs[0] - M);
+      num = __fmaf_rn(theirs[2 + tid], wgt, num);
+      den = __fmaf_rn(theirs[1], wgt, den);
+    }
+    if (split == 0) {  // the current position, from the freshly rotated key and the polled value row
+      const float4* k4 = reinterpret_cast<const float4*>(k_s);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int c = 0; c < (hs >> 2); ++c) {
+        const float4 kv = k4[c];
+        const float4 qv = q4[c];
+        a0 = __fmaf_rn(kv.x, qv.x, a0);
+        a1 = __fmaf_rn(kv.y, qv.y, a1);
+        a2 = __fmaf_rn(kv.z, qv.z, a2);
+        a3 = __fmaf_rn(kv.w, qv.w, a3);
+      }
+      const float s_pos = ((a0 + a1) + (a2 + a3)) * scale;
+      const float M_new = fmaxf(M, s_pos);
+      const float alpha = expf(M - M_new);
+      const float pp = expf(s_pos - M_new);
+      num = __fmaf_rn(num, alpha, pp * v_pos);
+      den = __fmaf_rn(den, alpha, pp);
+      M = M_new;
+    }
+    unsigned long long* area = P.scores + static_cast<size_t>(head) * seq_len;  // [SP][hs + 2] tagged words
+    if (split != 0) {
+      unsigned long long* mine = area + static_cast<size_t>(split) * (hs + 2);
+      st_tagged_gpu(mine + 2 + tid, num, tag_out);
+      if (tid == 0) st_tagged2_gpu(mine, M, den, tag_out);
+    } else {
+      const int active = min(SP, n_tiles);  // CTAs 1 .. active - 1 of the head had tiles
+      for (int sidx = 1; sidx < active; ++sidx) {
+        const unsigned long long* theirs = area + static_cast<size_t>(sidx) * (hs + 2);
+        unsigned long long w_m, w_l, w_o;
+        const long long t_start = clock64();
+        for (;;) {  // the three words in flight together
+          ld_tagged2_gpu(theirs, w_m, w_l);
+          w_o = ld_tagged_gpu(theirs + 2 + tid);
+          if (tag_of(w_m) == tag_out && tag_of(w_l) == tag_out && tag_of(w_o) == tag_out) break;
+          const unsigned seen = tag_of(w_o) != tag_out ? tag_of(w_o) : (tag_of(w_m) != tag_out ? tag_of(w_m) : tag_of(w_l));
+          poll_failed(seen, tag_out, t_start, 0);
+        }
+        const float ms = val_of(w_m), ls = val_of(w_l), os = val_of(w_o);
+        const float M_new = fmaxf(M, ms);
+        const float fa = expf(M - M_new), fb = expf(ms - M_new);
+        num = __fmaf_rn(num, fa, os * fb);
+        den = __fmaf_rn(den, fa, ls * fb);
+        M = M_new;
+      }
+      const float value = num / den;
+      if (ph.ta != nullptr)
+        st_tagged_gpu(ph.ta + static_cast<size_t>(head) * hs + tid, value, tag_out);
+      else
+        P.attn_out[static_cast<size_t>(head) * hs + tid] = value;
+    }
+  }
+  if (stamp && tid == 0) {
+    const long long c_end = clock64();
+    stamp[4] = static_cast<unsigned long long>(c_rope - c_begin);  // q/k/v poll + RoPE
+    stamp[5] = static_cast<unsigned long long>(c_sc);              // scores + online softmax (warp 0's blocks)
+    stamp[6] = static_cast<unsigned long long>(c_end - c_tiles);   // merges: warps, current row, other CTAs
+    stamp[7] = static_cast<unsigned long long>(c_pv);              // P.V (warp 0's blocks)
+    stamp[8] = static_cast<unsigned long long>(c_wait);            // ring waits
   }
   return pipe;
 }
@@ -1155,9 +1707,9 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
     if (sg.tag_out != nullptr) st_tagged_gpu(sg.tag_out + rr.row, v, hand_tag(ph.hand_out));
     if (sg.out == nullptr) {
     } else if (sg.head_major) {  // value cache [kv_head][SP][seq_len][dv]
-      const int hs = P.head_size, dv = hs / P.attn_split;
+      const int hs = P.head_size, dv = hs / P.attn_vsplit;
       const int kvh = rr.row / hs, d = rr.row % hs;
-      sg.out[((static_cast<size_t>(kvh) * P.attn_split + d / dv) * P.seq_len + pos) * dv + d % dv] = v;
+      sg.out[((static_cast<size_t>(kvh) * P.attn_vsplit + d / dv) * P.seq_len + pos) * dv + d % dv] = v;
     } else {
       sg.out[static_cast<long long>(pos) * sg.pos_stride + rr.row] = v;
     }
@@ -1354,7 +1906,7 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
           __syncwarp();
         }
         const Phase& ph = s_phase_prod;
-        if (ph.kind == kPhaseAttention || ph.kind == kPhaseAttnPV) {
+        if (ph.kind != kPhaseGemv) {
           const int SP = P.attn_split;
           if (cta >= P.head_num * SP || ppos == 0) continue;
           // rows t < pos of this head: final since the previous token.  Order the async-proxy
@@ -1373,7 +1925,35 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
           const int kvh = head / P.kv_mul;
           const size_t head_block =
               (static_cast<size_t>(ph.layer) * (P.kv_dim / hs) + kvh) * P.seq_len * hs;
-          if (ph.kind == kPhaseAttention) {  // K tiles j = split, split + SP, ...
+          if (ph.kind == kPhaseAttnFlash) {  // tiles j = split, split + SP, ...: K tile, then V tile
+            const int T = P.attn_tile;
+            const float* kbase = P.key_cache + head_block;
+            const float* vbase = P.value_cache + head_block;
+            const int n_tiles = attn_tiles(ppos, T);
+            for (int j = split; j < n_tiles; j += SP) {
+              const int t0 = j * T;
+              const int nt = min(T, ppos - t0);
+              for (int kv = 0; kv < 2; ++kv) {
+                mbar_wait(&empty_bar[pipe.slot], pipe.parity ^ 1u);
+                unsigned char* dst = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
+                if (lane == 0) mbar_expect_tx(&full_bar[pipe.slot], static_cast<uint32_t>(nt) * hs * 4);
+                __syncwarp();
+                if (kv == 0) {
+                  if (lane < (hs >> 2))
+                    bulk_g2s(dst + static_cast<size_t>(lane) * T * 16,
+                             kbase + (static_cast<size_t>(lane) * P.seq_len + t0) * 4,
+                             static_cast<uint32_t>(nt) * 16, &full_bar[pipe.slot], policy_kv);
+                } else if (lane == 0) {
+                  bulk_g2s(dst, vbase + static_cast<size_t>(t0) * hs, static_cast<uint32_t>(nt) * hs * 4,
+                           &full_bar[pipe.slot], policy_kv);
+                }
+                pipe.advance(S);
+                if (lane == 0) s_fill_count = ++filled; else ++filled;
+              }
+            }
+            continue;
+          }
+          if (ph.kind != kPhaseAttnPV) {  // K tiles j = split, split + SP, ... (fused: SP == 1, all of them)
             const int T = P.attn_tile;
             const float* kbase = P.key_cache + head_block;
             const int n_tiles = attn_tiles(ppos, T);
@@ -1391,7 +1971,8 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
               pipe.advance(S);
               if (lane == 0) s_fill_count = ++filled; else ++filled;
             }
-          } else {  // this CTA's slice of V: [seq_len][dv] contiguous
+          }
+          if (ph.kind != kPhaseAttention) {  // this CTA's slice of V: [seq_len][dv] contiguous
             const int dv = hs / SP, T = P.attn_tile_v;
             const float* vbase = P.value_cache + head_block + static_cast<size_t>(split) * P.seq_len * dv;
             const int n_tiles = attn_tiles(ppos, T);
@@ -1493,12 +2074,16 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
           __syncwarp();
         }
         const Phase& ph = s_phase_pf;
-        if (ph.kind == kPhaseAttention || ph.kind == kPhaseAttnPV) {
+        if (ph.kind != kPhaseGemv) {
           // KV tiles are L2-resident already (evict_last): count the producer's ring stages only
-          if (cta < P.head_num * P.attn_split && ppos > 0)
-            ahead += ph.kind == kPhaseAttention
-                         ? static_cast<unsigned>(own_tiles(attn_tiles(ppos, P.attn_tile), cta % P.attn_split, P.attn_split))
-                         : static_cast<unsigned>(attn_tiles(ppos, P.attn_tile_v));
+          if (cta < P.head_num * P.attn_split && ppos > 0) {
+            if (ph.kind == kPhaseAttnFlash)
+              ahead += 2u * static_cast<unsigned>(own_tiles(attn_tiles(ppos, P.attn_tile), cta % P.attn_split, P.attn_split));
+            else if (ph.kind != kPhaseAttnPV)
+              ahead += static_cast<unsigned>(own_tiles(attn_tiles(ppos, P.attn_tile), cta % P.attn_split, P.attn_split));
+            if (ph.kind == kPhaseAttnPV || ph.kind == kPhaseAttnFused)
+              ahead += static_cast<unsigned>(attn_tiles(ppos, P.attn_tile_v));
+          }
           continue;
         }
         const int u0 = static_cast<int>(static_cast<long long>(cta) * ph.units / G);
@@ -1587,14 +2172,18 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
           (PROF && prof_on) ? P.prof + (static_cast<size_t>(cta) * P.n_phases + pi) * kProfStamps : nullptr;
       if (stamp) stamp[0] = global_ns();
 
-      if (ph.kind == kPhaseAttention || ph.kind == kPhaseAttnPV) {
+      if (ph.kind != kPhaseGemv) {
         const int SP = P.attn_split;
         if (cta < P.head_num * SP) {
-          if (ph.kind == kPhaseAttention)
-            pipe = attention_scores_phase<CW>(P, cta / SP, cta % SP, pos, pipe, hand_tag(ph.hand_in), hand_tag(ph.hand_out));
+          if (ph.kind == kPhaseAttnFlash)
+            pipe = attention_flash_phase<CW>(P, cta / SP, cta % SP, pos, pipe, hand_tag(ph.hand_in), hand_tag(ph.hand_out), stamp);
+          else if (ph.kind == kPhaseAttnFused)
+            pipe = attention_fused_phase<CW>(P, cta, pos, pipe, hand_tag(ph.hand_in), hand_tag(ph.hand_out), stamp);
+          else if (ph.kind == kPhaseAttention)
+            pipe = attention_scores_phase<CW>(P, cta / SP, cta % SP, pos, pipe, hand_tag(ph.hand_in), hand_tag(ph.hand_out), stamp);
           else
             pipe = attention_pv_phase<CW>(P, cta / SP, cta % SP, pos, pipe, hand_tag(ph.hand_in), hand_tag(ph.hand_aux),
-                                          hand_tag(ph.hand_out));
+                                          hand_tag(ph.hand_out), stamp);
         }
         if (stamp) stamp[1] = stamp[2] = global_ns();
         if (ph.barrier_after) grid_barrier<CT>(P.barrier, bar_target, G);
@@ -1703,8 +2292,12 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   }
   // int8 arithmetic: "exact" reproduces the reference's fma(x * scale, float(w), acc) per element bit for
   // bit; "fast" (KLLM_INT8_MODE=fast) is the dp4a fixed-point mode (toleranced, ~3.5x fewer instructions)
-  int8_fast_ = 0;
-  if (const char* e = getenv("KLLM_INT8_MODE")) int8_fast_ = (int8 && std::string(e) == "fast") ? 1 : 0;
+  // The same switch frees the attention's summation order (flash-decoding, attention_flash_phase).
+  // kllm_decoder_desc::numerics picks the mode; KLLM_MODE=exact|fast (KLLM_INT8_MODE: older name) overrides.
+  fast_ = m.numerics == 1 ? 1 : 0;
+  for (const char* name : {"KLLM_INT8_MODE", "KLLM_MODE"})
+    if (const char* e = getenv(name)) fast_ = std::string(e) == "fast" ? 1 : 0;
+  int8_fast_ = (int8 && fast_) ? 1 : 0;
   kernel_ = kernel_for<false>(consumer_warps_, int8);
   kernel_prof_ = kernel_for<true>(consumer_warps_, int8);
   threads_ = consumer_warps_ * 32 + 64;
@@ -1727,9 +2320,6 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   int xbuf = max_in * 4;
   const int attn_ws = 2 * hs * 4;
   xbuf = std::max(xbuf, attn_ws);
-  xbuf = (xbuf + 127) & ~127;
-  const int xres = tagged_ ? ((dim * 4 + 127) & ~127) : 0;  // the CTA's copy of the residual stream
-  const int budget = max_smem - xbuf - xres - 2048;  // static shared memory + slack
   // Stage size: whole rows, so pick it to waste little of the ring on the model's row lengths.
   // fp32: 32 KB (4 rows of dim 2048, 2 of 4096).  int8: 27 KB = 6 rows of dim 4096 (+ scales) or
   // 2 rows of hidden 11008, which leaves six stages next to the 44 KB input vector and the 16 KB
@@ -1737,14 +2327,22 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   int stage_bytes = int8 ? 27 * 1024 : 32 * 1024;
   if (const char* e = getenv("KLLM_STAGE_BYTES")) stage_bytes = atoi(e);
   stage_bytes = (stage_bytes + 127) & ~127;
+  attn_tile_ = std::min(stage_bytes / (hs * 4), consumer_warps_ * 32) & ~31;  // one timestep per consumer thread
+  if (attn_tile_ < 32) return KLLM_E_UNSUPPORTED;
+  attn_parts_ = 1;
+  if (fast_) {  // flash attention: a lane quartet per timestep, warp partials (m, l, o[hs]) in the input buffer
+    if (hs & 15) return KLLM_E_UNSUPPORTED;
+    xbuf = std::max(xbuf, (2 * hs + consumer_warps_ * (hs + 2)) * 4);
+  }
+  xbuf = (xbuf + 127) & ~127;
+  const int xres = tagged_ ? ((dim * 4 + 127) & ~127) : 0;  // the CTA's copy of the residual stream
+  const int budget = max_smem - xbuf - xres - 2048;  // static shared memory + slack
   int stages = budget / stage_bytes;
   if (stages > mega::kMaxStages) stages = mega::kMaxStages;
   if (const char* e = getenv("KLLM_STAGES")) stages = std::min(stages, atoi(e));
   if (stages < 2) return KLLM_E_UNSUPPORTED;
   stage_bytes_ = stage_bytes;
   stages_ = stages;
-  attn_tile_ = std::min(stage_bytes / (hs * 4), consumer_warps_ * 32) & ~31;  // one timestep per consumer thread
-  if (attn_tile_ < 32) return KLLM_E_UNSUPPORTED;
   // attention split: SP CTAs per query head (power of two, <= 8), each owning head_size / SP output dims
   // (a multiple of 4 floats so that V slice rows stay 16-byte units for the bulk copies)
   if (m.seq_len & 3) return KLLM_E_UNSUPPORTED;
@@ -1752,11 +2350,23 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   while (attn_split_ * 2 <= 8 && m.head_num * attn_split_ * 2 <= grid_ && (hs / (attn_split_ * 2)) % 4 == 0 &&
          hs % (attn_split_ * 2) == 0)
     attn_split_ *= 2;
+  const int attn_split_max = attn_split_;
+  // The split costs one more hand-off per layer (~1.5 us): worth it when a head's K and V are big
+  // (head_size 128: 1 MB per head at context 1024), not for head_size 64 (measured, profiles/README.md).
+  if (hs < 128) attn_split_ = 1;
+  int split_cap = attn_split_max;
+  if (fast_) {  // flash: split by timestep, any power of two whose partial triples fit the scores area
+    attn_split_ = 1;
+    while (attn_split_ * 2 <= 8 && m.head_num * attn_split_ * 2 <= grid_ && attn_split_ * 2 * (hs + 2) <= m.seq_len)
+      attn_split_ *= 2;
+    split_cap = attn_split_;
+  }
   if (const char* e = getenv("KLLM_ATTN_SPLIT")) {
     const int v = atoi(e);
-    if (v >= 1 && v <= attn_split_ && (v & (v - 1)) == 0) attn_split_ = v;
+    if (v >= 1 && v <= split_cap && (v & (v - 1)) == 0) attn_split_ = v;
   }
-  attn_tile_v_ = (stage_bytes / ((hs / attn_split_) * 4)) & ~31;
+  attn_vsplit_ = fast_ ? 1 : attn_split_;
+  attn_tile_v_ = (stage_bytes / ((hs / attn_vsplit_) * 4)) & ~31;
   if (attn_tile_v_ < 32) return KLLM_E_UNSUPPORTED;
   xbuf_bytes_ = xbuf;
   xres_bytes_ = xres;
@@ -1884,32 +2494,58 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       close_phase(p, !handoffs);
       ph.push_back(p);
     }
-    int qkv_hand = 0;
-    {  // attention, scores: CTA (head, s) scores the K tiles s, s + SP, ... and publishes them tagged
+    if (fast_) {  // flash-decoding: attn_split_ CTAs per head by timestep, one phase
       Phase p{};
-      p.kind = mega::kPhaseAttention;
+      p.kind = mega::kPhaseAttnFlash;
       p.layer = l;
       if (handoffs) {
-        p.tq = t_q, p.tk = t_k, p.tv = t_v;
+        p.tq = t_q, p.tk = t_k, p.tv = t_v, p.ta = t_attn;
         p.hand_in = hands++;
+        p.hand_out = hands;
+      } else {
+        p.hand_out = hands++;  // the partial (m, l, o) triples are tagged words in every mode
       }
-      qkv_hand = p.hand_in;
-      p.hand_out = hands;  // the scores (always tagged words, also in the barrier modes)
       close_phase(p, !handoffs);
       ph.push_back(p);
-    }
-    {  // attention, softmax + P.V: CTA (head, s) owns output dims [s dv, (s + 1) dv)
+    } else if (attn_split_ == 1) {  // one CTA per head, one phase
       Phase p{};
-      p.kind = mega::kPhaseAttnPV;
+      p.kind = mega::kPhaseAttnFused;
       p.layer = l;
-      p.hand_in = hands++;
       if (handoffs) {
-        p.tv = t_v, p.ta = t_attn;
-        p.hand_aux = qkv_hand;
+        p.tq = t_q, p.tk = t_k, p.tv = t_v, p.ta = t_attn;
+        p.hand_in = hands++;
         p.hand_out = hands;
       }
       close_phase(p, !handoffs);
       ph.push_back(p);
+    } else {
+      int qkv_hand = 0;
+      {  // attention, scores: CTA (head, s) scores the K tiles s, s + SP, ... and publishes them tagged
+        Phase p{};
+        p.kind = mega::kPhaseAttention;
+        p.layer = l;
+        if (handoffs) {
+          p.tq = t_q, p.tk = t_k, p.tv = t_v;
+          p.hand_in = hands++;
+        }
+        qkv_hand = p.hand_in;
+        p.hand_out = hands;  // the scores (always tagged words, also in the barrier modes)
+        close_phase(p, !handoffs);
+        ph.push_back(p);
+      }
+      {  // attention, softmax + P.V: CTA (head, s) owns output dims [s dv, (s + 1) dv)
+        Phase p{};
+        p.kind = mega::kPhaseAttnPV;
+        p.layer = l;
+        p.hand_in = hands++;
+        if (handoffs) {
+          p.tv = t_v, p.ta = t_attn;
+          p.hand_aux = qkv_hand;
+          p.hand_out = hands;
+        }
+        close_phase(p, !handoffs);
+        ph.push_back(p);
+      }
     }
     {  // wo + residual (llama3.cpp:672-684)
       Phase p{};
@@ -1988,7 +2624,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   // The producer streams K/V rows written by the PREVIOUS token once the grid barrier that closed
   // that token's attention phase is passed; without such a barrier, the one that closed the token.
   for (Phase& p : ph)
-    if ((p.kind == mega::kPhaseAttention || p.kind == mega::kPhaseAttnPV) && !p.barrier_after) p.barrier_idx = bars;
+    if (p.kind != mega::kPhaseGemv && !p.barrier_after) p.barrier_idx = bars;
 
   if (cudaMalloc(&d_phases_, sizeof(Phase) * ph.size()) != cudaSuccess) return static_cast<int>(cudaErrorMemoryAllocation);
   cudaMemcpyAsync(d_phases_, ph.data(), sizeof(Phase) * ph.size(), cudaMemcpyHostToDevice, stream);
@@ -2048,6 +2684,8 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
   P.attn_tile = attn_tile_;
   P.attn_tile_v = attn_tile_v_;
   P.attn_split = attn_split_;
+  P.attn_vsplit = attn_vsplit_;
+  P.attn_parts = attn_parts_;
   P.scores = d_scores_;
   P.pf_stages = 8;  // 8 x 32 KB x 148 SMs = 38 MB of weights in flight towards L2 (measured: 6-12 best, >=24 thrashes L2)
   if (const char* e = getenv("KLLM_PREFETCH_STAGES")) P.pf_stages = std::max(0, atoi(e));

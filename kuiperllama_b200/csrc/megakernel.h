@@ -8,7 +8,13 @@
 namespace kllm {
 namespace mega {
 
-enum { kPhaseGemv = 0, kPhaseAttention = 1 /* scores of the split attention */, kPhaseAttnPV = 2 /* softmax + P.V */ };
+enum {
+  kPhaseGemv = 0,
+  kPhaseAttention = 1 /* scores of the split attention */,
+  kPhaseAttnPV = 2 /* softmax + P.V of the split attention */,
+  kPhaseAttnFused = 3 /* whole attention of one head in one CTA (attn_split == 1) */,
+  kPhaseAttnFlash = 4 /* toleranced: split by timestep, online softmax, partials merged by CTA 0 of the head */
+};
 constexpr int kProfStamps = 16;  // uint64 stamps per (CTA, phase) of kllm_decoder_profile
 
 struct Seg {
@@ -78,6 +84,8 @@ struct State {  // == StepState in decoder.cu
 struct Params {
   const Phase* phases;
   int n_phases, n_tokens;
+  int attn_vsplit;      // V cache layout [L][kv_head][attn_vsplit][seq_len][head_size / attn_vsplit]
+  int attn_parts;       // flash attention: threads per timestep in the scores pass
   int int8_fast;        // int8 weights: 1 = fixed-point activations on dp4a (toleranced), 0 = the reference's per-element order
   int skip_cls_tokens;  // the first skip_cls_tokens positions of this launch are prompt tokens: no classifier pass
   int num_stages, stage_bytes, xbuf_bytes;
@@ -150,6 +158,7 @@ struct MegaModel {
   int tp_world, tp_rank;
   unsigned long long* tp_data[8];
   int tp_stride;
+  int numerics;  // kllm_decoder_desc::numerics
 };
 
 class MegaEngine {
@@ -165,7 +174,9 @@ class MegaEngine {
   int stage_bytes() const { return stage_bytes_; }
   int phases() const { return n_phases_; }
   int attn_tile() const { return attn_tile_; }
-  int attn_split() const { return attn_split_; }
+  int attn_split() const { return attn_split_; }    // CTAs per query head
+  int attn_vsplit() const { return attn_vsplit_; }  // slices of the V cache layout
+  bool fast() const { return fast_ != 0; }
   int consumer_warps() const { return consumer_warps_; }
   bool int8_fast() const { return int8_fast_ != 0; }
 
@@ -187,6 +198,8 @@ class MegaEngine {
   int attn_split_ = 1, attn_tile_v_ = 0;
   unsigned long long* d_scores_ = nullptr;  // tagged scores of the split attention
   int int8_fast_ = 0;
+  int fast_ = 0;  // numerics: 0 = bit-exact with the reference, 1 = toleranced (free summation order)
+  int attn_vsplit_ = 1, attn_parts_ = 1;
   const void* kernel_ = nullptr;       // decode_megakernel<consumer warps, int8, false>
   const void* kernel_prof_ = nullptr;  // ... <.., true>: records the phase timeline stamps
   int n_barriers_per_token_ = 0;

@@ -143,7 +143,7 @@ class Decoder:
     """Owns a ``kllm_decoder`` built over torch-held device weights."""
 
     def __init__(self, shape: ModelShape, weights: dict, stream=None, tp_size=1, tp_rank=0,
-                 allreduce=None, allreduce_ctx=None, full_dim=None, comm=None):
+                 allreduce=None, allreduce_ctx=None, full_dim=None, comm=None, numerics="exact"):
         self.lib = load_library()
         self.shape = shape
         self.weights = weights  # keep the tensors alive
@@ -177,6 +177,8 @@ class Decoder:
         if "bq" in weights:
             d.bq, d.bk, d.bv = (per_layer(weights[n]) for n in ("bq", "bk", "bv"))
         d.tp_size, d.tp_rank = tp_size, tp_rank
+        # "exact": bit-identical to the reference; "fast": toleranced (kllm_b200.h, kllm_decoder_desc::numerics)
+        d.numerics = {"exact": 0, "fast": 1}[numerics]
         if allreduce is not None:
             d.allreduce = allreduce
             d.allreduce_ctx = allreduce_ctx

@@ -90,6 +90,11 @@ class LLama2Model : public Model {
   mutable std::vector<int32_t> last_tokens_;
   mutable const float* last_embeddings_ = nullptr;
   mutable bool logits_in_decoder_ = false;
+  // leading positions of the current sequence present in the decoder's KV cache / in the layer
+  // path's kKeyCache+kValueCache (the two are separate allocations with different layouts)
+  mutable int32_t decoder_rows_ = 0;
+  mutable int32_t layer_rows_ = 0;
+  base::Status sync_layer_cache(int32_t pos) const;
 };
 }  // namespace model
 #endif  // KLLM_KUIPER_MODEL_LLAMA3_H_

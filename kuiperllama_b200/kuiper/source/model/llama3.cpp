@@ -399,17 +399,22 @@ base::Status LLama2Model::predict(const tensor::Tensor& input, const tensor::Ten
   if (input.is_empty()) return base::error::InvalidArgument("The input tensor is empty.");
   const int32_t pos = pos_tensor.index<int32_t>(0);
   // Is `input` a row of the last embedding() result?  Then its token id is known and the whole
-  // step runs in the fused decoder.
+  // step runs in the fused decoder.  The decoder and the layer-by-layer path keep separate KV
+  // caches; decoder_rows_ / layer_rows_ count the leading positions each one holds, and a step is
+  // only routed to a path whose cache has every row below `pos` (sync_layer_cache() copies the
+  // decoder's rows over when the layer path has to continue a sequence the decoder started).
   const float* p = input.ptr<float>();
   if (decoder_ != nullptr && last_embeddings_ != nullptr && p >= last_embeddings_) {
     const ptrdiff_t delta = p - last_embeddings_;
     const ptrdiff_t row = delta / config_->dim_;
-    if (delta % config_->dim_ == 0 && row < static_cast<ptrdiff_t>(last_tokens_.size())) {
+    const bool rows_present = pos <= decoder_rows_ || pos > layer_rows_;  // else only the layer path has them
+    if (delta % config_->dim_ == 0 && row < static_cast<ptrdiff_t>(last_tokens_.size()) && rows_present) {
       int32_t nxt = -1;
       const int rc = kllm_decoder_step(decoder_, last_tokens_[row], pos, is_prompt ? 1 : 0, &nxt);
       if (rc != 0) return base::error::InternalError(std::string("kllm_decoder_step: ") + kllm_error_string(rc));
       next = nxt;
       logits_in_decoder_ = true;
+      if (pos <= decoder_rows_) decoder_rows_ = pos + 1;  // rows above pos belong to an older sequence
       return base::error::Success();
     }
   }
@@ -419,10 +424,31 @@ base::Status LLama2Model::predict(const tensor::Tensor& input, const tensor::Ten
   return base::error::Success();
 }
 
+// Rows [0, pos) of the sequence live in the fused decoder's cache but not (all) in the layer path's:
+// copy them over (reference layout [layer][seq_len][kv_dim], llama3.cpp:469-475) so that forward()
+// attends over the same history.  Rare path (a caller that hands predict()/forward() a tensor that
+// is not an embedding() row in the middle of a sequence): a blocking round trip through the host.
+base::Status LLama2Model::sync_layer_cache(int32_t pos) const {
+  if (decoder_ == nullptr || pos <= layer_rows_ || decoder_rows_ < pos) return base::error::Success();
+  const tensor::Tensor& kc = get_buffer(ModelBufferType::kKeyCache);
+  const tensor::Tensor& vc = get_buffer(ModelBufferType::kValueCache);
+  std::vector<float> kh(kc.size()), vh(vc.size());
+  const int rc = kllm_decoder_read_kv(decoder_, kh.data(), vh.data());
+  if (rc != 0) return base::error::InternalError(std::string("kllm_decoder_read_kv: ") + kllm_error_string(rc));
+  cudaStreamSynchronize(cuda_config_->stream);
+  if (cudaMemcpy(const_cast<float*>(kc.ptr<float>()), kh.data(), kc.byte_size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(const_cast<float*>(vc.ptr<float>()), vh.data(), vc.byte_size(), cudaMemcpyHostToDevice) != cudaSuccess)
+    return base::error::InternalError("copying the decoder's KV rows to the layer path's cache failed");
+  layer_rows_ = decoder_rows_;
+  return base::error::Success();
+}
+
 // ---- the layer-by-layer path (reference orchestration, llama3.cpp:147-167, 600-745) -------------------
 base::Status LLama2Model::forward(const tensor::Tensor& input, const tensor::Tensor& pos_tensor, int& next) const {
   UNUSED(next);
   if (input.is_empty()) return base::error::InvalidArgument("The input tensor is empty.");
+  const int32_t pos = pos_tensor.index<int32_t>(0);
+  if (base::Status st = sync_layer_cache(pos); !st) return st;
   for (int32_t l = 0; l < config_->layer_num_; ++l) {
     attention_rms(l, input);
     attention_qkv(l, pos_tensor);
@@ -431,6 +457,7 @@ base::Status LLama2Model::forward(const tensor::Tensor& input, const tensor::Ten
   }
   cls_logits(input);
   logits_in_decoder_ = false;
+  if (pos <= layer_rows_) layer_rows_ = pos + 1;
   return base::error::Success();
 }
 

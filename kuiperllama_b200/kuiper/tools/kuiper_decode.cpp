@@ -2,13 +2,16 @@
 // drives it with text (embedding -> fill_input -> predict per position).
 //
 //   kuiper_decode <checkpoint> <llama|qwen> <fp32|int8> <n_steps> <id0> [id1 ...]
-//                 [--layers] [--logits out.f32]
+//                 [--layers] [--copy-at K] [--logits out.f32]
 //
 // ids are the prompt; after the prompt the model free-runs greedily until n_steps positions
 // have been processed.  Prints the id chosen at every position (-1 for prompt steps before the
 // last prompt token) on one line.  --layers uses Model::forward (layer-by-layer op registry path)
-// instead of predict's fused decoder.  --logits writes the last position's logits as raw fp32.
+// instead of predict's fused decoder.  --copy-at K hands predict() a COPY of the embedding row at
+// position K (so that step cannot be recognised and runs layer by layer in the middle of a sequence
+// the fused decoder started).  --logits writes the last position's logits as raw fp32.
 #include <base/base.h>
+#include <cuda_runtime_api.h>
 #include <glog/logging.h>
 
 #include <cstdio>
@@ -23,16 +26,18 @@
 int main(int argc, char** argv) {
   if (argc < 6) {
     std::fprintf(stderr, "usage: %s <checkpoint> <llama|qwen> <fp32|int8> <n_steps> <id0> [id1 ...] "
-                         "[--layers] [--logits out.f32]\n", argv[0]);
+                         "[--layers] [--copy-at K] [--logits out.f32]\n", argv[0]);
     return 2;
   }
   const std::string checkpoint = argv[1], family = argv[2], prec = argv[3];
   const int n_steps = std::atoi(argv[4]);
   std::vector<int> prompt;
   bool layers = false;
+  int copy_at = -1;
   std::string logits_path;
   for (int i = 5; i < argc; ++i) {
     if (!std::strcmp(argv[i], "--layers")) layers = true;
+    else if (!std::strcmp(argv[i], "--copy-at") && i + 1 < argc) copy_at = std::atoi(argv[++i]);
     else if (!std::strcmp(argv[i], "--logits") && i + 1 < argc) logits_path = argv[++i];
     else prompt.push_back(std::atoi(argv[i]));
   }
@@ -60,7 +65,16 @@ int main(int argc, char** argv) {
   std::vector<int> chosen;
   auto run = [&](const tensor::Tensor& input, bool is_prompt) {
     if (!layers) {
-      STATUS_CHECK(m->predict(input, pos_tensor, is_prompt, next));
+      if (pos_tensor.index<int32_t>(0) == copy_at) {
+        // the row is a view into the model's embedding buffer: copy it into storage of its own
+        tensor::Tensor copy(base::DataType::kDataTypeFp32, static_cast<int32_t>(input.size()), true,
+                            base::CUDADeviceAllocatorFactory::get_instance());
+        CHECK(cudaMemcpy(copy.ptr<float>(), input.ptr<float>(), input.byte_size(), cudaMemcpyDeviceToDevice) ==
+              cudaSuccess);
+        STATUS_CHECK(m->predict(copy, pos_tensor, is_prompt, next));
+      } else {
+        STATUS_CHECK(m->predict(input, pos_tensor, is_prompt, next));
+      }
       return;
     }
     STATUS_CHECK(m->forward(input, pos_tensor, next));

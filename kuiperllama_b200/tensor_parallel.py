@@ -193,12 +193,12 @@ class Comm:
             self.handle = None
 
 
-def make_tp_decoder(shape: ModelShape, full_weights: dict, comm: Comm, stream=None) -> Decoder:
+def make_tp_decoder(shape: ModelShape, full_weights: dict, comm: Comm, stream=None, numerics="exact") -> Decoder:
     """Decoder for this rank's shard of `full_weights` (every rank passes the same full dict,
     e.g. synth_weights with the same seed; the shard is cut here and the rest can be freed)."""
     tp, rank = comm.world, comm.rank
     if tp == 1:
-        return Decoder(shape, full_weights, stream=stream)
+        return Decoder(shape, full_weights, stream=stream, numerics=numerics)
     shard = shard_weights(shape, full_weights, tp, rank)
     return Decoder(local_shape(shape, tp, rank), shard, stream=stream, tp_size=tp, tp_rank=rank,
-                   comm=comm, full_dim=shape.dim)
+                   comm=comm, full_dim=shape.dim, numerics=numerics)

@@ -385,25 +385,31 @@ def test_prompt_call_equals_stepping(kllm_lib, key):
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("key,steps", [("small-int8", 64), ("small-tp-int8", 64), ("llama2-7b-int8", 96)])
-def test_int8_fast_mode_within_north_star_tolerance(kllm_lib, monkeypatch, key, steps):
-    """KLLM_INT8_MODE=fast (persistent engine): activations as 24-bit fixed point per 64-group, int8
-    weights x int8 digits on dp4a.  TOLERANCED against the bit-exact mode (which the tests above pin to
-    the reference's CUDA path): teacher-forced on the exact mode's tokens, logits within 1e-4
-    (north-star tolerance) at every position and the same greedy id wherever the exact top-2 margin
-    exceeds 2e-4; also full-size Llama-2-7B int8 (BASELINE.json configs[2])."""
+@pytest.mark.parametrize("key,steps,stage_bytes", [
+    ("small-int8", 64, None), ("small-tp-int8", 64, None), ("small-int8", 90, 8192),
+    ("small", 150, 4096),        # fp32, head_size 32: 32-timestep tiles -> 5 tiles over 4 CTAs per head
+    ("small-qwen", 120, 8192),   # qwen RoPE pairing, q/k/v biases; 32-timestep tiles, one CTA per head
+    ("tinyllama-1.1b", 700, None),  # BASELINE.json configs[1]: 128-timestep tiles, GQA 8:1
+    ("llama2-7b-int8", 200, None)])  # configs[2]: dp4a rows + 32-timestep tiles, 16 threads per timestep
+def test_fast_numerics_within_north_star_tolerance(kllm_lib, monkeypatch, key, steps, stage_bytes):
+    """numerics="fast" (persistent engine): int8 rows as 24-bit fixed-point activations x int8 weights
+    on dp4a, attention as flash-decoding (split by timestep over several CTAs per head, online softmax,
+    partials merged).  TOLERANCED against the bit-exact mode (which the tests above pin to the
+    reference's CUDA path): teacher-forced on the exact mode's tokens, logits within 1e-4 (north-star
+    tolerance) at every position and the same greedy id wherever the exact top-2 margin exceeds 2e-4."""
     from kuiperllama_b200 import SHAPES, Decoder, synth_weights
     monkeypatch.setenv("KLLM_ENGINE", "persistent")
+    if stage_bytes:
+        monkeypatch.setenv("KLLM_STAGE_BYTES", str(stage_bytes))
     if key in _FULL_CACHE or key == "llama2-7b-int8":
         case = _full_size_case(key, 1236)
         shape, w = case["shape"], case["w"]
     else:
         shape = SHAPES[key]
         w = synth_weights(shape, "cuda", 31)
-    monkeypatch.setenv("KLLM_INT8_MODE", "exact")
     exact = Decoder(shape, w)
-    monkeypatch.setenv("KLLM_INT8_MODE", "fast")
-    fast = Decoder(shape, w)
+    fast = Decoder(shape, w, numerics="fast")
+    assert exact.engine == fast.engine == "persistent"
     tok, worst, checked = 1, 0.0, 0
     for pos in range(steps):
         a = exact.step(tok, pos)
@@ -420,3 +426,28 @@ def test_int8_fast_mode_within_north_star_tolerance(kllm_lib, monkeypatch, key, 
     # free-running determinism of the fast mode
     assert fast.generate(1, 0, 32) == fast.generate(1, 0, 32)
     exact.close(); fast.close()
+
+
+def test_fast_numerics_by_environment(kllm_lib, monkeypatch):
+    """KLLM_MODE=fast overrides the descriptor's numerics at create time (and KLLM_MODE=exact a
+    descriptor that asks for fast)."""
+    from kuiperllama_b200 import SHAPES, Decoder, synth_weights
+    monkeypatch.setenv("KLLM_ENGINE", "persistent")
+    shape = SHAPES["small-int8"]
+    w = synth_weights(shape, "cuda", 31)
+    exact = Decoder(shape, w)
+    monkeypatch.setenv("KLLM_MODE", "fast")
+    by_env = Decoder(shape, w)
+    monkeypatch.setenv("KLLM_MODE", "exact")
+    forced_exact = Decoder(shape, w, numerics="fast")
+    monkeypatch.delenv("KLLM_MODE")
+    by_desc = Decoder(shape, w, numerics="fast")
+    for pos in range(40):
+        t = exact.step(1 + pos, pos)
+        for d in (by_env, forced_exact, by_desc):
+            d.step(1 + pos, pos)
+    assert_bit_equal(exact.logits(), forced_exact.logits(), "KLLM_MODE=exact")
+    assert_bit_equal(by_env.logits(), by_desc.logits(), "KLLM_MODE=fast vs numerics=fast")
+    assert not np.array_equal(exact.logits(), by_env.logits())
+    for d in (exact, by_env, forced_exact, by_desc):
+        d.close()

@@ -244,3 +244,52 @@ def test_tp_decoder_matches_unsharded_oracle(kllm_lib, oracle, tmp_path, key, wo
             assert np.array_equal(got["peer", "persistent", r], ref)
     if key in ("small-tp", "small-tp-int8", "small-qwen"):
         assert ("peer", "persistent") in modes, "the persistent engine must take this shape"
+
+
+def _fast_rank(rank, world, key, steps, teacher, out_dir):
+    import os
+    os.environ["KLLM_ENGINE"] = "persistent"
+    import torch
+    from kuiperllama_b200 import SHAPES, synth_weights
+    from kuiperllama_b200.tensor_parallel import Comm, make_tp_decoder
+    shape = SHAPES[key]
+    full = synth_weights(shape, "cuda", 11)
+    comm = Comm(shape.dim, "peer")
+    dec = make_tp_decoder(shape, full, comm, numerics="fast")
+    assert dec.engine == "persistent"
+    torch.distributed.barrier()
+    logits = []
+    for pos in range(steps):
+        dec.step(teacher[pos], pos)
+        logits.append(dec.logits())
+    np.savez(f"{out_dir}/fast_rank{rank}.npz", logits=np.stack(logits))
+    dec.close()
+    comm.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key,world", [("small-tp", 2), ("small-tp-int8", 2), ("small-tp", 4)])
+def test_tp_fast_numerics_within_tolerance_of_unsharded_exact(kllm_lib, tmp_path, key, world, monkeypatch):
+    """Tensor parallel + numerics="fast" (flash-decoding attention over the rank's local heads, dp4a
+    int8 rows): teacher-forced on the UNSHARDED exact decoder's tokens, every rank's logits stay within
+    the north-star tolerance of the unsharded exact decoder at every position, and all ranks hold
+    identical bits (rank-ordered sums)."""
+    _need_gpus(world)
+    from kuiperllama_b200 import SHAPES, Decoder, synth_weights
+    monkeypatch.setenv("KLLM_ENGINE", "persistent")
+    monkeypatch.setenv("KLLM_STAGE_BYTES", "8192")  # 32-timestep attention tiles: several tiles, several CTAs per head
+    steps = 80
+    shape = SHAPES[key]
+    one = Decoder(shape, synth_weights(shape, "cuda", 11))
+    tok, teacher, want = 1, [], []
+    for pos in range(steps):
+        teacher.append(tok)
+        tok = one.step(tok, pos)
+        want.append(one.logits())
+    one.close()
+    spawn(_fast_rank, world, "nccl", (key, steps, teacher, str(tmp_path)))
+    got = [np.load(tmp_path / f"fast_rank{r}.npz")["logits"] for r in range(world)]
+    worst = max(float(np.abs(got[0][pos] - want[pos]).max()) for pos in range(steps))
+    assert 0.0 < worst <= TOL, worst
+    for r in range(1, world):
+        assert np.array_equal(got[r].view(np.uint32), got[0].view(np.uint32))

@@ -31,10 +31,12 @@ def ensure_built(variant):
     return exe
 
 
-def run_decode(variant, checkpoint, family, prec, n_steps, ids, layers=False, logits=None, env=None):
+def run_decode(variant, checkpoint, family, prec, n_steps, ids, layers=False, logits=None, env=None, copy_at=None):
     cmd = [str(ensure_built(variant)), str(checkpoint), family, prec, str(n_steps), *map(str, ids)]
     if layers:
         cmd.append("--layers")
+    if copy_at is not None:
+        cmd += ["--copy-at", str(copy_at)]
     if logits is not None:
         cmd += ["--logits", str(logits)]
     return subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
@@ -155,3 +157,23 @@ def test_cpp_free_running_decode_identical_to_cabi(kllm_lib, tmp_path, key, vari
         chosen = [int(x) for x in r.stdout.split()]
         assert chosen[len(prompt) - 1:] == want, ("layers" if layers else "fused")
     dec.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("copy_at", [0, 3, 9])
+def test_cpp_predict_keeps_one_history_when_a_step_leaves_the_fused_decoder(kllm_lib, tmp_path, copy_at):
+    """predict() runs in the fused decoder when it recognises its input as an embedding() row and
+    layer by layer otherwise; the two keep separate KV caches.  A sequence that leaves the decoder in
+    the middle (position K gets a COPY of the row) must still attend over the whole history: the
+    decoder's rows are copied into the layer path's cache, later positions stay on the layer path.
+    Ids and final logits are bit-identical to the uninterrupted fused run."""
+    name = "tiny_llama2_fp32"
+    g = np.load(GOLDEN / f"{name}.npz")
+    toks = [int(t) for t in g["tokens"]][:4]
+    n = 14
+    a, b = tmp_path / "a.f32", tmp_path / "b.f32"
+    r0 = run_decode("llama2", GOLDEN / f"{name}.bin", "llama", "fp32", n, toks, logits=a)
+    r1 = run_decode("llama2", GOLDEN / f"{name}.bin", "llama", "fp32", n, toks, logits=b, copy_at=copy_at)
+    assert r0.returncode == 0 and r1.returncode == 0, r0.stderr + r1.stderr
+    assert r0.stdout.split() == r1.stdout.split()
+    assert np.array_equal(np.fromfile(a, dtype=np.uint32), np.fromfile(b, dtype=np.uint32))

@@ -5,6 +5,7 @@
 """
 import argparse
 import ctypes
+import os
 import sys
 from pathlib import Path
 
@@ -41,8 +42,8 @@ def main():
     L = shape.layer_num
     print(f"# {shape.name}: phase timeline of the decode step at pos {a.pos} (us, globaltimer), grid {G}, {P} phases")
     print(f"# token time (first phase entered -> last barrier passed): {st[:, -1, 3].max():.1f} us")
-    names = ["qkv", "scores", "attn_pv", "wo", "w1w3", "w2"]
-    NPL = len(names)  # phases per layer
+    NPL = (P - 1) // L  # phases per layer: 5 with the fused attention, 6 with the split one
+    names = ["qkv", "attn", "wo", "w1w3", "w2"] if NPL == 5 else ["qkv", "scores", "attn_pv", "wo", "w1w3", "w2"]
     stage = (st[:, :, 1] - st[:, :, 0])          # input staging (+norm)
     work = (st[:, :, 2] - st[:, :, 1])           # consuming ring stages (or attention)
     bar = (st[:, :, 3] - st[:, :, 2])            # waiting at the grid barrier
@@ -52,19 +53,24 @@ def main():
     print(f"{'phase':>10} {'count':>5} {'phase_us':>9} {'stage_x':>8} {'(poll)':>7} {'work_med':>9} {'work_max':>9} {'barrier_min':>11} "
           f"{'barrier_med':>11} | warp 0 of the median CTA, us: {'ringwait':>8} {'dots':>6} {'reduce':>6} {'epilog':>6} {'addend':>6}")
 
-    def row(nm, idx):
-        c = np.median(cyc[:, idx], axis=0).mean(axis=0) / ghz / 1e3 if len(idx) > 1 else np.median(cyc[:, idx], axis=0)[0] / ghz / 1e3
+    def row(nm, idx, ctas=slice(None)):
+        c = np.median(cyc[ctas][:, idx], axis=0).mean(axis=0) / ghz / 1e3 if len(idx) > 1 else np.median(cyc[ctas][:, idx], axis=0)[0] / ghz / 1e3
         print(f"{nm:>10} {len(idx):5d} {dur[idx].mean():9.2f} {np.median(stage[:, idx]):8.2f} {np.median(poll[:, idx]):7.2f} {np.median(work[:, idx]):9.2f} "
               f"{work[:, idx].max(axis=0).mean():9.2f} {bar[:, idx].min(axis=0).mean():11.2f} {np.median(bar[:, idx]):11.2f} | "
               f"{'':32s}{c[4]:8.2f} {c[1]:6.2f} {c[2]:6.2f} {c[3]:6.2f} {c[0]:6.2f}")
+    fast = os.environ.get("KLLM_MODE") == "fast"
+    sp = int(os.environ.get("KLLM_ATTN_SPLIT_SHOWN", "0")) or (4 if (NPL == 6 or fast) else 1)
     for k, nm in enumerate(names):
-        row(nm, [l * NPL + k for l in range(L)])
+        attn_row = nm in ("attn", "scores", "attn_pv")
+        row(nm, [l * NPL + k for l in range(L)], slice(0, shape.head_num * sp) if attn_row else slice(None))
     row("cls", [P - 1])
+    print("# attention rows (thread 0 of the median ATTENTION CTA): ringwait = K/V tile waits, dots = scores, reduce = softmax, "
+          "epilog = P.V, addend = input polls (+RoPE)")
     # with tagged hand-overs most phases have no barrier: `barrier_*` is then ~0 and the wait for the
     # previous phase's outputs shows up in `stage_x` of the consuming phase (the poll loop)
     heads = shape.head_num
     ai = [l * NPL + 1 for l in range(L)]
-    pvi = [l * NPL + 2 for l in range(L)]
+    pvi = [l * NPL + (2 if NPL == 6 else 1) for l in range(L)]
     attn = (st[:heads, pvi, 2] - st[:heads, ai, 0])
     print(f"# attention (scores + softmax + P.V) on the first {heads} attention CTAs: median {np.median(attn):.2f} us, slowest head per layer (mean) "
           f"{attn.max(axis=0).mean():.2f} us")
