@@ -264,6 +264,12 @@ const float* kllm_decoder_logits_device(const kllm_decoder* dec);
 int kllm_decoder_read_kv(kllm_decoder* dec, float* key_host, float* value_host);
 /* Kernel launches one decode step issues (graph nodes; 1 for the persistent engine). */
 int kllm_decoder_launches_per_step(const kllm_decoder* dec);
+/* Classifier rows THIS rank streams per token: vocab_size, or vocab_size / tp_size when the
+ * tensor-parallel persistent engine shards the classifier by vocabulary (cls_logits,
+ * llama3.cpp:722-731, computed once across the ranks instead of once per rank).  That needs a
+ * kllm_comm created with max_count >= max(dim, vocab_size / tp_size): the ranks publish their
+ * logits rows through the same tagged exchange area as the o_proj / down_proj partials. */
+int kllm_decoder_classifier_rows(const kllm_decoder* dec);
 /* "persistent": one cooperative megakernel launch runs whole positions with a TMA-fed weight
  * ring; "graph": CUDA-graph chain of fused launches (shapes the ring does not handle, tensor
  * parallel).  Environment KLLM_ENGINE=graph|persistent forces a choice at create time. */

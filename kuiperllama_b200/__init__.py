@@ -102,6 +102,7 @@ _SIGNATURES = {
     "kllm_decoder_logits_device": (c_void_p, [c_void_p]),
     "kllm_decoder_read_kv": (c_int, [c_void_p, c_void_p, c_void_p]),
     "kllm_decoder_launches_per_step": (c_int, [c_void_p]),
+    "kllm_decoder_classifier_rows": (c_int, [c_void_p]),
     "kllm_decoder_engine": (c_char_p, [c_void_p]),
     "kllm_decoder_profile": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32,
                                      POINTER(c_int32), POINTER(c_int32)]),

@@ -654,6 +654,10 @@ int kllm_decoder_read_kv(kllm_decoder* dc, float* key_host, float* value_host) {
   return 0;
 }
 int kllm_decoder_launches_per_step(const kllm_decoder* dc) { return dc ? dc->launches_per_step : 0; }
+int kllm_decoder_classifier_rows(const kllm_decoder* dc) {
+  if (!dc) return 0;
+  return dc->use_mega ? dc->mega.cls_rows() : dc->d.vocab_size;
+}
 const char* kllm_decoder_engine(const kllm_decoder* dc) {
   if (!dc) return "";
   return dc->use_mega ? "persistent" : "graph";

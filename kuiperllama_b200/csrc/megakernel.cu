@@ -185,6 +185,23 @@ __device__ __noinline__ void poll_failed(unsigned seen, unsigned want, long long
     __trap();
   }
 }
+__device__ __forceinline__ unsigned long long ld_tagged_sys(const unsigned long long* p) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
+}
+// spin until the word (written by any rank) carries `tag`
+__device__ __forceinline__ float poll_tagged_sys(const unsigned long long* p, unsigned tag) {
+  unsigned long long w = ld_tagged_sys(p);
+  if (tag_of(w) != tag) {
+    const long long t0 = clock64();
+    do {
+      poll_failed(tag_of(w), tag, t0, 1);
+      w = ld_tagged_sys(p);
+    } while (tag_of(w) != tag);
+  }
+  return val_of(w);
+}
 // spin until the word carries `tag`
 __device__ __forceinline__ float poll_tagged(const unsigned long long* p, unsigned tag) {
   unsigned long long w = ld_tagged_gpu(p);
@@ -1690,7 +1707,7 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
       return;
     }
     if (ph.tp_out) {
-      const unsigned tag = P.tp_seq_base + static_cast<unsigned>(tok * P.exch_per_token + ph.exch) + 1u;
+      const unsigned tag = P.tp_seq_base + static_cast<unsigned>(tok * P.exch_per_token + ph.exch_out) + 1u;
       const size_t off = (static_cast<size_t>(tag & 1u) * P.tp_world + P.tp_rank) * P.tp_stride + unit;
       if (P.tp_world == 1) {
         st_tagged_gpu(P.tp_data[0] + off, d0, tag);
@@ -1855,6 +1872,51 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
   return Carry{pipe, best.v, best.i};
 }
 
+// ---- tensor parallel, classifier sharded by vocabulary ----------------------------------------------
+// Rank r computed logits rows [r V/W, (r+1) V/W) and published them as tagged words into EVERY rank's
+// exchange area (the tp_out epilogue, exchange `ph.exch`).  Here the CTAs of this rank split the V
+// words of the local area between them: poll, store the logit, keep (max, lowest index).  All ranks
+// end with the same full logits vector and the same per-CTA partials, hence the same greedy id --
+// the cross-rank argmax needs no further exchange.
+template <int CW>
+__device__ __noinline__ void gather_logits_phase(const Params& P, int tok) {
+  constexpr int CT = CW * 32;
+  const Phase& ph = g_ph_cons;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cta = blockIdx.x, G = gridDim.x;
+  const int V = ph.units, rows = ph.in_dim;  // rows per rank
+  const unsigned tag = P.tp_seq_base + static_cast<unsigned>(tok * P.exch_per_token + ph.exch) + 1u;
+  const unsigned long long* area =
+      P.tp_data[P.tp_rank] + static_cast<size_t>(tag & 1u) * P.tp_world * P.tp_stride;
+  const int u0 = static_cast<int>(static_cast<long long>(cta) * V / G);
+  const int u1 = static_cast<int>(static_cast<long long>(cta + 1) * V / G);
+  float* logits = ph.seg[0].out;
+  ArgBest best{0.f, -1};
+  for (int i = u0 + tid; i < u1; i += CT) {
+    const int r = i / rows, j = i - r * rows;
+    const float v = poll_tagged_sys(area + static_cast<size_t>(r) * P.tp_stride + j, tag);
+    logits[i] = v;
+    arg_fold(best, v, i);
+  }
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const float ov = __shfl_xor_sync(kFull, best.v, off);
+    const int oi = __shfl_xor_sync(kFull, best.i, off);
+    arg_fold(best, ov, oi);
+  }
+  if (lane == 0) {
+    g_s_argv[warp] = best.v;
+    g_s_argi[warp] = best.i;
+  }
+  consumer_sync<CT>();
+  if (tid == 0) {
+    ArgBest b{0.f, -1};
+    for (int w = 0; w < CW; ++w) arg_fold(b, g_s_argv[w], g_s_argi[w]);
+    P.arg_val[cta] = b.v;
+    P.arg_idx[cta] = b.i;
+  }
+}
+
 // ---- the kernel ---------------------------------------------------------------------------------
 template <int CW, bool INT8, bool PROF>
 __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Params P) {
@@ -1896,7 +1958,7 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
     unsigned filled = 0u;
     int ppos = P.state->pos;
     for (int tok = 0; tok < P.n_tokens; ++tok, ++ppos) {
-      const int n_run = tok < P.skip_cls_tokens ? P.n_phases - 1 : P.n_phases;  // prompt token: no classifier
+      const int n_run = tok < P.skip_cls_tokens ? P.n_phases - P.n_cls_phases : P.n_phases;  // prompt token: no classifier
       for (int pi = 0; pi < n_run; ++pi) {
         {
           const uint32_t* src = reinterpret_cast<const uint32_t*>(P.phases + pi);
@@ -1906,6 +1968,7 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
           __syncwarp();
         }
         const Phase& ph = s_phase_prod;
+        if (ph.kind == kPhaseGather) continue;  // nothing to stream
         if (ph.kind != kPhaseGemv) {
           const int SP = P.attn_split;
           if (cta >= P.head_num * SP || ppos == 0) continue;
@@ -2064,7 +2127,7 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
     unsigned ahead = 0u;  // stages walked by this warp (same counting as the producer's `filled`)
     int ppos = P.state->pos;
     for (int tok = 0; tok < P.n_tokens; ++tok, ++ppos) {
-      const int n_run = tok < P.skip_cls_tokens ? P.n_phases - 1 : P.n_phases;
+      const int n_run = tok < P.skip_cls_tokens ? P.n_phases - P.n_cls_phases : P.n_phases;
       for (int pi = 0; pi < n_run; ++pi) {
         {
           const uint32_t* src = reinterpret_cast<const uint32_t*>(P.phases + pi);
@@ -2074,6 +2137,7 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
           __syncwarp();
         }
         const Phase& ph = s_phase_pf;
+        if (ph.kind == kPhaseGather) continue;
         if (ph.kind != kPhaseGemv) {
           // KV tiles are L2-resident already (evict_last): count the producer's ring stages only
           if (cta < P.head_num * P.attn_split && ppos > 0) {
@@ -2172,6 +2236,14 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
           (PROF && prof_on) ? P.prof + (static_cast<size_t>(cta) * P.n_phases + pi) * kProfStamps : nullptr;
       if (stamp) stamp[0] = global_ns();
 
+      if (ph.kind == kPhaseGather) {
+        if (!(tok < P.skip_cls_tokens)) gather_logits_phase<CW>(P, tok);
+        if (stamp) stamp[1] = stamp[2] = global_ns();
+        if (ph.barrier_after) grid_barrier<CT>(P.barrier, bar_target, G);
+        prev_barrier = ph.barrier_after != 0;
+        if (stamp) stamp[3] = global_ns();
+        continue;
+      }
       if (ph.kind != kPhaseGemv) {
         const int SP = P.attn_split;
         if (cta < P.head_num * SP) {
@@ -2196,7 +2268,7 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Param
       // A prompt token (llama3.cpp:733-745: predict(..., is_prompt = true) discards the logits and
       // returns -1) skips the classifier -- its weights are not even streamed -- but keeps the grid
       // barrier that closes the token.
-      if (!(ph.argmax && tok < P.skip_cls_tokens)) {
+      if (!(ph.cls && tok < P.skip_cls_tokens)) {
         const Carry out = gemv_phase<CW, INT8, PROF>(P, Carry{pipe, best.v, best.i}, tok, pos, emb_row, stamp);
         pipe = out.pipe;
         best.v = out.best_v, best.i = out.best_i;
@@ -2456,7 +2528,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   auto output_adds_to_x = [&](Phase& p, bool first_layer) {
     if (tagged_) {
       p.tp_out = 1;
-      p.exch = exch++;
+      p.exch_out = exch++;
       p.residual = nullptr;
       p.residual_from_emb = 0;
       close_phase(p, false);
@@ -2610,12 +2682,43 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
     input_is_x(p);
     p.norm_w = m.final_norm;
     p.norm_eps = eps;
-    p.seg[0] = {m.wcls, int8 ? m.scls : nullptr, nullptr, m.logits, 0, m.vocab_size, 0};
-    p.units = m.vocab_size;
-    p.argmax = 1;
-    if (int rc = plan(p)) return rc;
-    close_phase(p, true);
-    ph.push_back(p);
+    p.cls = 1;
+    // Tensor parallel: shard the classifier by vocabulary when the exchange area can carry a rank's
+    // rows (kllm_comm_create(max_count >= vocab / world)); every rank still holds the whole matrix and
+    // reads only its rows.  KLLM_TP_SHARD_CLS=0 keeps it replicated.
+    const char* shard_env = getenv("KLLM_TP_SHARD_CLS");
+    const bool shard = W > 1 && m.vocab_size % W == 0 && m.tp_stride >= m.vocab_size / W &&
+                       !(shard_env && atoi(shard_env) == 0);
+    cls_rows_ = shard ? m.vocab_size / W : m.vocab_size;
+    n_cls_phases_ = shard ? 2 : 1;
+    if (shard) {
+      const size_t row0 = static_cast<size_t>(m.tp_rank) * cls_rows_;
+      p.seg[0] = {static_cast<const unsigned char*>(m.wcls) + row0 * dim * wb,
+                  int8 ? m.scls + row0 * (dim / m.group_size) : nullptr, nullptr, nullptr, 0, cls_rows_, 0};
+      p.units = cls_rows_;
+      if (int rc = plan(p)) return rc;
+      p.tp_out = 1;  // rows go to every rank's exchange area as tagged words
+      p.exch_out = exch++;
+      close_phase(p, false);
+      ph.push_back(p);
+      Phase g{};
+      g.kind = mega::kPhaseGather;
+      g.cls = 1;
+      g.argmax = 1;
+      g.units = m.vocab_size;
+      g.in_dim = cls_rows_;
+      g.exch = p.exch_out;
+      g.seg[0].out = m.logits;
+      close_phase(g, true);
+      ph.push_back(g);
+    } else {
+      p.seg[0] = {m.wcls, int8 ? m.scls : nullptr, nullptr, m.logits, 0, m.vocab_size, 0};
+      p.units = m.vocab_size;
+      p.argmax = 1;
+      if (int rc = plan(p)) return rc;
+      close_phase(p, true);
+      ph.push_back(p);
+    }
   }
   n_phases_ = static_cast<int>(ph.size());
   n_barriers_per_token_ = bars;
@@ -2676,6 +2779,7 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
   P.n_phases = n_phases_;
   P.n_tokens = n_tokens;
   P.skip_cls_tokens = skip_cls_tokens;
+  P.n_cls_phases = n_cls_phases_;
   P.int8_fast = int8_fast_;
   P.num_stages = stages_;
   P.stage_bytes = stage_bytes_;

@@ -13,7 +13,8 @@ enum {
   kPhaseAttention = 1 /* scores of the split attention */,
   kPhaseAttnPV = 2 /* softmax + P.V of the split attention */,
   kPhaseAttnFused = 3 /* whole attention of one head in one CTA (attn_split == 1) */,
-  kPhaseAttnFlash = 4 /* toleranced: split by timestep, online softmax, partials merged by CTA 0 of the head */
+  kPhaseAttnFlash = 4 /* toleranced: split by timestep, online softmax, partials merged by CTA 0 of the head */,
+  kPhaseGather = 5 /* tensor parallel, classifier sharded by vocabulary: collect every rank's logits, argmax partials */
 };
 constexpr int kProfStamps = 16;  // uint64 stamps per (CTA, phase) of kllm_decoder_profile
 
@@ -39,6 +40,7 @@ struct Phase {
   int n_seg;
   int swiglu;             // units are (w1 row, w3 row) pairs -> SiLU*gate epilogue
   int argmax;             // track (max, index) of the produced rows (classifier)
+  int cls;                // classifier work: skipped for prompt positions (llama3.cpp:733-745 discards their logits)
   int x_from_emb;         // input vector is the embedding row of the current token
   int residual_from_emb;  // residual source is the embedding row (layer 0)
   int group_size, group_shift;
@@ -60,7 +62,9 @@ struct Phase {
   //           own shared-memory copy of the residual stream (it starts as the embedding row of the
   //           token and is updated by every exchange), so the stream never round-trips through
   //           global memory between CTAs.
-  int tp_in, tp_out, exch;
+  int tp_in, tp_out;
+  int exch;      // index (within the token) of the exchange tp_in consumes
+  int exch_out;  // ... of the exchange tp_out publishes (a phase may do both: the sharded classifier)
   int barrier_after;      // 1: a grid barrier closes the phase
   int barrier_idx;        // barriers of this token passed once this phase is closed
   // Local tagged hand-offs (same words, one rank): the phase's input vector is polled from tag_in
@@ -87,6 +91,7 @@ struct Params {
   int attn_vsplit;      // V cache layout [L][kv_head][attn_vsplit][seq_len][head_size / attn_vsplit]
   int attn_parts;       // flash attention: threads per timestep in the scores pass
   int int8_fast;        // int8 weights: 1 = fixed-point activations on dp4a (toleranced), 0 = the reference's per-element order
+  int n_cls_phases;     // trailing phases that make up the classifier (1, or 2 with the vocabulary-sharded form)
   int skip_cls_tokens;  // the first skip_cls_tokens positions of this launch are prompt tokens: no classifier pass
   int num_stages, stage_bytes, xbuf_bytes;
   int xres_bytes;  // shared-memory copy of the residual stream behind the input vector (tagged modes; else 0)
@@ -177,6 +182,7 @@ class MegaEngine {
   int attn_split() const { return attn_split_; }    // CTAs per query head
   int attn_vsplit() const { return attn_vsplit_; }  // slices of the V cache layout
   bool fast() const { return fast_ != 0; }
+  int cls_rows() const { return cls_rows_; }  // classifier rows this rank streams per token
   int consumer_warps() const { return consumer_warps_; }
   bool int8_fast() const { return int8_fast_ != 0; }
 
@@ -200,6 +206,7 @@ class MegaEngine {
   int int8_fast_ = 0;
   int fast_ = 0;  // numerics: 0 = bit-exact with the reference, 1 = toleranced (free summation order)
   int attn_vsplit_ = 1, attn_parts_ = 1;
+  int cls_rows_ = 0, n_cls_phases_ = 1;
   const void* kernel_ = nullptr;       // decode_megakernel<consumer warps, int8, false>
   const void* kernel_prof_ = nullptr;  // ... <.., true>: records the phase timeline stamps
   int n_barriers_per_token_ = 0;

@@ -211,6 +211,11 @@ class Decoder:
         return self.lib.kllm_decoder_launches_per_step(self.handle)
 
     @property
+    def classifier_rows(self) -> int:
+        """Classifier rows this rank streams per token (vocab / tp when sharded by vocabulary)."""
+        return self.lib.kllm_decoder_classifier_rows(self.handle)
+
+    @property
     def engine(self) -> str:
         return self.lib.kllm_decoder_engine(self.handle).decode()
 

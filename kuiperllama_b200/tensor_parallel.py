@@ -88,13 +88,23 @@ def local_shape(shape: ModelShape, tp: int, rank: int = 0) -> ModelShape:
                    kv_head_num=len(kv_heads_of_rank(shape, tp, rank)), hidden_dim=len(ffn_range(shape, tp, rank)))
 
 
-def weight_bytes_per_token_per_gpu(shape: ModelShape, tp: int, rank: int = 0) -> int:
+def comm_words(shape: ModelShape, world: int) -> int:
+    """max_count for Comm / kllm_comm_create: the residual exchange needs `dim` words per rank; with
+    room for vocab / world more, the persistent engine shards the classifier by vocabulary."""
+    per_rank = -(-shape.vocab_size // max(world, 1))
+    return max(shape.dim, per_rank if shape.vocab_size % max(world, 1) == 0 else 0)
+
+
+def weight_bytes_per_token_per_gpu(shape: ModelShape, tp: int, rank: int = 0, classifier_rows: int | None = None) -> int:
     """ALGORITHMIC bytes ONE rank streams per decode step: its shard of every layer matmul
-    (+ int8 scales) plus what is replicated (classifier, norm vectors, one embedding row)."""
+    (+ int8 scales), its classifier rows (`classifier_rows`: Decoder.classifier_rows; default all,
+    i.e. replicated) plus what is replicated (norm vectors, one embedding row)."""
     if tp == 1:
         return shape.weight_bytes_per_token()
     s = shape
     d, L, V, hs = s.dim, s.layer_num, s.vocab_size, s.head_size
+    if classifier_rows:
+        V = classifier_rows
     kv_rows = len(kv_heads_of_rank(s, tp, rank)) * hs
     numel = L * (2 * d * d // tp + 2 * kv_rows * d + 3 * len(ffn_range(s, tp, rank)) * d) + V * d
     wbytes = numel * 4 if s.group_size == 0 else numel + numel // s.group_size * 4

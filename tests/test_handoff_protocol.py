@@ -48,9 +48,17 @@ class Rank:
 
 class Config:
     def __init__(self, world=1, ctas=4, heads=2, kv_heads=1, layers=2, tokens=3, exch_slots=2, x_bufs=2,
-                 dim=None, ffn=None):
+                 dim=None, ffn=None, cls_shard=False, prompt_tokens=0):
         self.world, self.ctas, self.heads, self.kv_heads = world, ctas, heads, kv_heads
         self.layers, self.tokens, self.exch_slots, self.x_bufs = layers, tokens, exch_slots, x_bufs
+        # tensor parallel, classifier sharded by vocabulary: one more exchange per token (each rank
+        # publishes its logits rows to every rank; a gather step polls them before the grid barrier),
+        # which makes the number of exchanges per token ODD -- the slot parity flips from token to token
+        self.cls_shard = cls_shard
+        # the first `prompt_tokens` positions are prompt positions: the classifier is skipped (nobody
+        # consumes the token's last W2 exchange), only the grid barrier that closes the token stays
+        self.prompt_tokens = prompt_tokens
+        self.exch_per_token = 2 * layers + (1 if cls_shard else 0)
         self.hq = 2  # elements per head
         # residual stream / FFN width; by default not a multiple of the CTA count on purpose.  Small
         # models have FEWER rows than the GPU has CTAs, so some CTAs own no rows of a phase at all.
@@ -81,7 +89,7 @@ def cta_program(cfg, ranks, r, c, stats):
 
     def stage_residual(tok, e):
         """Input staging of a phase that consumes the residual stream after exchange e (tp_in)."""
-        tag = tok * 2 * L + e + 1
+        tag = tok * cfg.exch_per_token + e + 1
         slot = tag % cfg.exch_slots
         mine = split(cfg.dim, G, c)
         for i in range(cfg.dim):
@@ -100,7 +108,7 @@ def cta_program(cfg, ranks, r, c, stats):
         stats["staged"] += 1
 
     def publish_exchange(tok, e):
-        tag = tok * 2 * L + e + 1
+        tag = tok * cfg.exch_per_token + e + 1
         slot = tag % cfg.exch_slots
         for i in split(cfg.dim, G, c):
             for k in range(1, W + 1):  # every rank's area, own last
@@ -148,7 +156,19 @@ def cta_program(cfg, ranks, r, c, stats):
                     raise ProtocolError(f"W2 read {v}")
             yield from publish_exchange(tok, 2 * l + 1)
         # ---- classifier: consumes x after the last exchange; then the one grid barrier of the token
-        yield from stage_residual(tok, 2 * L - 1)
+        if tok >= cfg.prompt_tokens:
+            yield from stage_residual(tok, 2 * L - 1)
+        if cfg.cls_shard and tok >= cfg.prompt_tokens:
+            # this rank's logits rows (the model reuses `dim` as the rows per rank) go to every rank as
+            # exchange 2L; the gather splits the world x dim words of the local area over the CTAs
+            yield from publish_exchange(tok, 2 * L)
+            tag = tok * cfg.exch_per_token + 2 * L + 1
+            slot = tag % cfg.exch_slots
+            for i in split(W * cfg.dim, G, c):
+                src, j = divmod(i, cfg.dim)
+                v = yield from poll(me.exch[slot][src], j, tag, f"rank {r} logits of rank {src}")
+                if v != ("partial", tok, 2 * L, src):
+                    raise ProtocolError(f"rank {r} cta {c}: logit {i} holds {v}")
         yield "store"
         me.barrier += 1
         while me.barrier < (tok + 1) * G:
@@ -192,6 +212,17 @@ CONFIGS = {
     # tiny models on a big GPU: most CTAs own no q|k|v row, some no row of the residual stream either
     "1 rank, more CTAs than rows": Config(world=1, ctas=12, heads=2, kv_heads=1, dim=7, ffn=9),
     "2 ranks, more CTAs than rows": Config(world=2, ctas=9, heads=2, kv_heads=2, dim=5, ffn=11, tokens=2),
+    # classifier sharded by vocabulary: an odd number of exchanges per token
+    "2 ranks, sharded classifier": Config(world=2, ctas=4, heads=2, kv_heads=2, tokens=4, cls_shard=True),
+    "3 ranks, sharded classifier, one layer": Config(world=3, ctas=3, heads=2, kv_heads=1, layers=1, tokens=4, cls_shard=True),
+    "2 ranks, sharded classifier, more CTAs than rows": Config(world=2, ctas=9, heads=2, kv_heads=2, dim=5, ffn=11,
+                                                               tokens=3, cls_shard=True),
+    # a prompt in one launch: classifier skipped for its positions (kllm_decoder_prompt)
+    "1 rank, prompt positions": Config(world=1, ctas=5, heads=2, kv_heads=1, tokens=5, prompt_tokens=3),
+    "2 ranks, sharded classifier, prompt positions": Config(world=2, ctas=4, heads=2, kv_heads=2, tokens=5,
+                                                            cls_shard=True, prompt_tokens=3),
+    "2 ranks, sharded classifier, prompt positions, more CTAs than rows":
+        Config(world=2, ctas=9, heads=2, kv_heads=2, dim=5, ffn=11, tokens=4, cls_shard=True, prompt_tokens=2),
 }
 
 
@@ -222,6 +253,8 @@ def test_checker_catches_a_single_slot_exchange():
     _must_fail(Config(world=1, ctas=12, heads=2, kv_heads=1, dim=7, ffn=9, exch_slots=1), "a single-slot exchange")
     _must_fail(Config(world=2, ctas=9, heads=2, kv_heads=2, dim=5, ffn=11, tokens=2, exch_slots=1),
                "a single-slot exchange across ranks")
+    _must_fail(Config(world=2, ctas=9, heads=2, kv_heads=2, dim=5, ffn=11, tokens=3, exch_slots=1, cls_shard=True),
+               "a single-slot exchange with the sharded classifier")
 
 
 def test_checker_catches_a_single_residual_buffer():

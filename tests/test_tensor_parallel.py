@@ -174,10 +174,10 @@ def _decoder_rank(rank, world, key, backend, engine, steps, out_dir):
     os.environ["KLLM_ENGINE"] = engine
     import torch
     from kuiperllama_b200 import SHAPES, KllmError, synth_weights
-    from kuiperllama_b200.tensor_parallel import Comm, make_tp_decoder
+    from kuiperllama_b200.tensor_parallel import Comm, comm_words, make_tp_decoder
     shape = SHAPES[key]
     full = synth_weights(shape, "cuda", 11)
-    comm = Comm(shape.dim, backend)
+    comm = Comm(comm_words(shape, world), backend)  # room for vocab / world words per rank
     try:
         dec = make_tp_decoder(shape, full, comm)
     except KllmError as e:
@@ -188,6 +188,9 @@ def _decoder_rank(rank, world, key, backend, engine, steps, out_dir):
         comm.close()
         return
     assert dec.engine == engine
+    # persistent engine: the classifier is sharded by vocabulary (each rank streams vocab / world rows and
+    # publishes them to every rank); the graph engine keeps it replicated
+    assert dec.classifier_rows == (shape.vocab_size // world if engine == "persistent" else shape.vocab_size)
     torch.distributed.barrier()  # the ranks' kernels wait for each other's partial sums: start together
     ids = dec.generate(1, 0, steps)
     logits = dec.logits()

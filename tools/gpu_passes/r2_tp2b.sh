@@ -1,0 +1,9 @@
+#!/bin/bash
+# round 2, 2 GPUs: classifier sharded by vocabulary (tagged gather) -- TP decoder tests + bench.py --gpus 2
+set -u
+mkdir -p gpurun_out
+O=gpurun_out/r2tp2b
+timeout 1200 python -m pytest tests/test_tensor_parallel.py -m gpu -x -q -k "tp_decoder or tp_fast" > ${O}_pytest.log 2>&1; echo "pytest tp rc=$?"; tail -8 ${O}_pytest.log | cut -c1-220
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --steps 64 --warmup 3 --reps 3 > ${O}_bench.json 2> ${O}_bench.err; echo "bench tp2 rc=$?"; tail -3 ${O}_bench.err | cut -c1-300
+python -c "
+import json;d=json.load(open('${O}_bench.json'));print(round(d['value'],1),round(d['e2e']['value'],1),d['by_position_tok_s'],round(d['roofline']['frac'],3),d['config'].get('classifier_rows_per_gpu'),d.get('parity'));x=d.get('exact');print('exact',x and (round(x['value'],1),round(x['roofline_frac'],3)));s=d.get('secondary');print('secondary',s and (round(s['value'],1),round(s['e2e']['value'],1),round(s['roofline']['frac'],3),s.get('parity')))"
