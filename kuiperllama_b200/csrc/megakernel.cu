@@ -546,10 +546,12 @@ __device__ __noinline__ void quantize_input_inplace(float* xs, int M, int tid) {
   for (int base = 0; base < quarters; base += CT) {  // CT % 32 == 0: whole warps, groups never straddle one
     const int qg = base + tid;
     const bool on = qg < quarters;
+    // lanes past the end read the last quarter again (their group is entirely past the end: M % 64 == 0),
+    // so v[] is always written and stays in registers instead of local memory
     float4 v[4];
     float gmax = 0.f;
-    if (on) {
-      const float4* g4 = reinterpret_cast<const float4*>(xs) + qg * 4;
+    {
+      const float4* g4 = reinterpret_cast<const float4*>(xs) + min(qg, quarters - 1) * 4;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         v[j] = g4[j];
@@ -1451,6 +1453,9 @@ __device__ KLLM_STAGE_CALL float stage_exchange(const unsigned long long* area, 
   float ssq = 0.f;
   const long long t_start = clock64();
   for (int pb = t; pb < n4; pb += NT * UP) {
+    // Every slot of the batch loads SOMETHING (slots past the end re-read the last pack): a buffer
+    // with conditionally written elements is kept in local memory by the compiler, and with the ring
+    // taking the whole unified L1 a local-memory access is an L2 round trip per poll round.
     unsigned long long wd[UP][W][4];
     bool ok;
     unsigned seen = tag;
@@ -1458,34 +1463,29 @@ __device__ KLLM_STAGE_CALL float stage_exchange(const unsigned long long* area, 
       ok = true;
 #pragma unroll
       for (int k = 0; k < UP; ++k) {
-        const int p = pb + k * NT;
-        if (p < n4) {
+        const int p = min(pb + k * NT, n4 - 1);
 #pragma unroll
-          for (int r = 0; r < W; ++r) {
-            const unsigned long long* row = area + static_cast<size_t>(r) * tp_stride + 4 * p;
-            if (W == 1) {
-              ld_tagged2_gpu(row, wd[k][r][0], wd[k][r][1]);
-              ld_tagged2_gpu(row + 2, wd[k][r][2], wd[k][r][3]);
-            } else {
-              ld_tagged2(row, wd[k][r][0], wd[k][r][1]);
-              ld_tagged2(row + 2, wd[k][r][2], wd[k][r][3]);
-            }
+        for (int r = 0; r < W; ++r) {
+          const unsigned long long* row = area + static_cast<size_t>(r) * tp_stride + 4 * p;
+          if (W == 1) {
+            ld_tagged2_gpu(row, wd[k][r][0], wd[k][r][1]);
+            ld_tagged2_gpu(row + 2, wd[k][r][2], wd[k][r][3]);
+          } else {
+            ld_tagged2(row, wd[k][r][0], wd[k][r][1]);
+            ld_tagged2(row + 2, wd[k][r][2], wd[k][r][3]);
           }
         }
       }
 #pragma unroll
-      for (int k = 0; k < UP; ++k) {
-        if (pb + k * NT < n4) {
+      for (int k = 0; k < UP; ++k)
 #pragma unroll
-          for (int r = 0; r < W; ++r)
+        for (int r = 0; r < W; ++r)
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (tag_of(wd[k][r][e]) != tag) {
-                ok = false;
-                seen = tag_of(wd[k][r][e]);
-              }
-        }
-      }
+          for (int e = 0; e < 4; ++e)
+            if (tag_of(wd[k][r][e]) != tag) {
+              ok = false;
+              seen = tag_of(wd[k][r][e]);
+            }
       if (!ok) poll_failed(seen, tag, t_start, 1);
     } while (!ok);
 #pragma unroll
@@ -1524,28 +1524,25 @@ __device__ __forceinline__ void stage_handoff_inline(const unsigned long long* s
                                                      float4* xs4) {
   const long long t_start = clock64();
   for (int pb = t; pb < n4; pb += NT * UP) {
-    unsigned long long wd[UP][4];
+    unsigned long long wd[UP][4];  // every slot loads (clamped index): keeps the buffer in registers, see stage_exchange
     bool ok;
     unsigned seen = tag;
     do {
       ok = true;
 #pragma unroll
       for (int k = 0; k < UP; ++k) {
-        const int p = pb + k * NT;
-        if (p < n4) {
-          ld_tagged2_gpu(src + 4 * p, wd[k][0], wd[k][1]);
-          ld_tagged2_gpu(src + 4 * p + 2, wd[k][2], wd[k][3]);
-        }
+        const int p = min(pb + k * NT, n4 - 1);
+        ld_tagged2_gpu(src + 4 * p, wd[k][0], wd[k][1]);
+        ld_tagged2_gpu(src + 4 * p + 2, wd[k][2], wd[k][3]);
       }
 #pragma unroll
       for (int k = 0; k < UP; ++k)
-        if (pb + k * NT < n4)
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (tag_of(wd[k][e]) != tag) {
-              ok = false;
-              seen = tag_of(wd[k][e]);
-            }
+        for (int e = 0; e < 4; ++e)
+          if (tag_of(wd[k][e]) != tag) {
+            ok = false;
+            seen = tag_of(wd[k][e]);
+          }
       if (!ok) poll_failed(seen, tag, t_start, 2);
     } while (!ok);
 #pragma unroll
@@ -1919,7 +1916,7 @@ __device__ __noinline__ void gather_logits_phase(const Params& P, int tok) {
 
 // ---- the kernel ---------------------------------------------------------------------------------
 template <int CW, bool INT8, bool PROF>
-__global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const Params P) {
+__global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const __grid_constant__ Params P) {
   constexpr int CT = CW * 32;  // consumer threads
   uint64_t* full_bar = g_full_bar;
   uint64_t* empty_bar = g_empty_bar;
