@@ -1598,6 +1598,22 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
   const bool has_norm = ph.norm_w != nullptr;
   float ssq = 0.f;
   bool ssq_ready = false;
+  // The RMSNorm weight of the phase does not depend on anything: fetch this thread's packs from L2
+  // BEFORE polling the input, so their latency (~0.4 us) hides behind the poll instead of following it.
+  // Fat-warp builds only (the thin int8 build has no registers to park them in); vectors too long for
+  // kNormPre packs per thread are read after the poll as before.  Slots past the end re-read the last
+  // pack so that the buffer is always written (stays in registers).
+  constexpr int kNormPre = CW <= 6 ? 3 : (CW <= 8 ? 2 : 0);
+  const bool norm_pre = kNormPre > 0 && has_norm && n4 <= kNormPre * CT;
+  float4 nw_pre[kNormPre > 0 ? kNormPre : 1];
+  if (kNormPre > 0 && norm_pre) {
+    const float4* nw4 = reinterpret_cast<const float4*>(ph.norm_w);
+#pragma unroll
+    for (int k = 0; k < kNormPre; ++k) nw_pre[k] = __ldg(nw4 + min(tid + k * CT, n4 - 1));
+  } else {
+#pragma unroll
+    for (int k = 0; k < (kNormPre > 0 ? kNormPre : 1); ++k) nw_pre[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   if (ph.tp_in) {
     // x = x_old + (p_0 + ... + p_{W-1}); no grid barrier, no all-reduce kernel
     const unsigned tag = P.tp_seq_base + static_cast<unsigned>(tok * P.exch_per_token + ph.exch) + 1u;
@@ -1609,7 +1625,7 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
         // buffers of a deeper batch would spill, and a spill is an L2 round trip here; the sum of
         // squares is then taken from shared memory.  Few fat warps: the 128 rmsnorm threads poll four
         // packs each and fold the sum of squares into the same pass.
-        if (CW >= 16) {
+        if (CW >= 12) {
           stage_exchange<1, 2, false>(area, P.tp_stride, tag, n4, tid, CT, xs4w, xres4);
         } else if (has_norm) {
           if (tid < kNormThreads)
@@ -1624,7 +1640,7 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
       default: stage_exchange<8, 1, false>(area, P.tp_stride, tag, n4, tid, CT, xs4w, xres4); break;
     }
   } else if (ph.tag_in != nullptr) {
-    if (CW >= 16)
+    if (CW >= 12)
       stage_handoff<2>(ph.tag_in, hand_tag(ph.hand_in), n4, tid, CT, xs4w);
     else
       stage_handoff<4>(ph.tag_in, hand_tag(ph.hand_in), n4, tid, CT, xs4w);
@@ -1659,14 +1675,20 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
       // scale is known: keeping it in registers across the poll made ptxas spill, and with the ring
       // taking all of shared memory a spill is an L2 round trip too
       const float4* nw4 = reinterpret_cast<const float4*>(ph.norm_w);
-      for (int i = tid; i < n4; i += CT) {
-        const float4 nw = __ldg(nw4 + i);
+      auto scale_pack = [&](int i, const float4& nw) {
         float4 v = xs4w[i];
         v.x = __fmul_rn(__fmul_rn(sc, v.x), nw.x);
         v.y = __fmul_rn(__fmul_rn(sc, v.y), nw.y);
         v.z = __fmul_rn(__fmul_rn(sc, v.z), nw.z);
         v.w = __fmul_rn(__fmul_rn(sc, v.w), nw.w);
         xs4w[i] = v;
+      };
+      if (kNormPre > 0 && norm_pre) {
+#pragma unroll
+        for (int k = 0; k < kNormPre; ++k)
+          if (tid + k * CT < n4) scale_pack(tid + k * CT, nw_pre[k]);
+      } else {
+        for (int i = tid; i < n4; i += CT) scale_pack(i, __ldg(nw4 + i));
       }
     }
   }
@@ -1739,8 +1761,12 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
     // Rows per task (compile-time knob KLLM_TASK_ROWS: 1, 2 or 4).  A CTA owns only 14-83 rows of a
     // phase and every consumer warp has to pass (wait + arrive) every ring stage in order, so a warp
     // sitting on a fat task while its neighbours have none holds up the refill of the whole ring.
-    constexpr int kTaskRows = KLLM_TASK_ROWS;
-    const int upt = ph.swiglu ? (kTaskRows >= 2 ? kTaskRows / 2 : 1) : kTaskRows;  // units per task
+    // The host picks the rows per task of each phase (MegaEngine::init, pick_task_rows): short phases
+    // whose rows are already in the ring when they start are as slow as their slowest warp, so they
+    // want many small tasks; long ones want fat tasks that share the loads of the input vector.
+    constexpr int kTaskRows = KLLM_TASK_ROWS;  // upper bound (compile time: which dot_rows<> forms exist)
+    const int task_rows = min(kTaskRows, max(1, ph.task_rows));
+    const int upt = ph.swiglu ? (task_rows >= 2 ? task_rows / 2 : 1) : task_rows;  // units per task
     int task = 0;                      // tasks of this phase so far (same count in every warp)
     for (int u = u0; u < u1; u += ups) {
       const int n = min(ups, u1 - u);
@@ -1750,7 +1776,7 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
       cyc_wait += c1 - c0;
       const unsigned char* sbase = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
       for (int i0 = 0; i0 < n; i0 += upt, ++task) {
-        if ((task & (CW - 1)) != warp) continue;
+        if (task % CW != warp) continue;  // CW is 6, 8 or 16: a real modulo (a mask would idle warps 2 and 3 of 6)
         const int nu = min(upt, n - i0);
         const long long t_a = stamp ? clock64() : 0;
         float bias_v = 0.f, res_v = 0.f;
@@ -1812,7 +1838,7 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
     // consecutive stages; chunk boundaries are multiples of 128 packs so every virtual
     // thread still sees its packs in increasing order.
     for (int u = u0; u < u1; ++u) {
-      const bool mine = ((u - u0) & (CW - 1)) == warp;
+      const bool mine = (u - u0) % CW == warp;
       float bias_v = 0.f, res_v = 0.f;
       if (mine && lane == 0) prefetch_addend(u, bias_v, res_v);
       float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
@@ -2201,6 +2227,9 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const __gri
   int pos = P.state->pos;
   int step = P.state->step;
   float4* xres4 = reinterpret_cast<float4*>(xres);
+  constexpr int kPhaseWords = static_cast<int>(sizeof(Phase) / 4);
+  static_assert(kPhaseWords <= CT, "phase copy: one word per consumer thread");
+  uint32_t next_phase_word = tid < kPhaseWords ? __ldg(reinterpret_cast<const uint32_t*>(P.phases) + tid) : 0u;
 
   for (int tok = 0; tok < P.n_tokens; ++tok) {
     const float* emb_row = P.tok_emb + static_cast<size_t>(token) * P.dim;
@@ -2222,11 +2251,13 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const __gri
         // the grid barrier that ended the previous phase is the hazard fence for this copy; a
         // phase closed by a tagged exchange has none, so fence the CTA's own warps here
         if (!prev_barrier) consumer_sync<CT>();
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(P.phases + pi);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&s_phase_cons);
-        static_assert(sizeof(Phase) / 4 <= CT, "phase copy");
-        if (tid < static_cast<int>(sizeof(Phase) / 4)) dst[tid] = __ldg(src + tid);
+        if (tid < kPhaseWords) dst[tid] = next_phase_word;
         consumer_sync<CT>();
+        // ... and the descriptor of the phase after this one starts its way from L2 now (one word per
+        // thread), so that its latency hides behind this phase instead of opening the next
+        const int npi = pi + 1 == P.n_phases ? 0 : pi + 1;
+        if (tid < kPhaseWords) next_phase_word = __ldg(reinterpret_cast<const uint32_t*>(P.phases + npi) + tid);
       }
       const Phase& ph = s_phase_cons;
       unsigned long long* stamp =
@@ -2313,6 +2344,7 @@ template <bool PROF>
 const void* kernel_for(int consumer_warps, bool int8) {
   if (int8) {
     if (consumer_warps == 16) return reinterpret_cast<const void*>(mega::decode_megakernel<16, true, PROF>);
+    if (consumer_warps == 14) return reinterpret_cast<const void*>(mega::decode_megakernel<14, true, PROF>);
     if (consumer_warps == 6) return reinterpret_cast<const void*>(mega::decode_megakernel<6, true, PROF>);
     return reinterpret_cast<const void*>(mega::decode_megakernel<8, true, PROF>);
   }
@@ -2356,7 +2388,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   consumer_warps_ = int8 ? 16 : 6;
   if (const char* e = getenv("KLLM_CONSUMER_WARPS")) {
     const int v = atoi(e);
-    if (int8 && (v == 6 || v == 8 || v == 16)) consumer_warps_ = v;  // fast mode: CT >= 192 quantises M <= 16384 in <= 6 rounds
+    if (int8 && (v == 6 || v == 8 || v == 14 || v == 16)) consumer_warps_ = v;  // fast mode: CT >= 192 quantises M <= 16384 in <= 6 rounds
     if (!int8 && (v == 6 || v == 8)) consumer_warps_ = v;
   }
   // int8 arithmetic: "exact" reproduces the reference's fma(x * scale, float(w), acc) per element bit for
@@ -2443,6 +2475,37 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
 
   // ---- phase table ---------------------------------------------------------------------------------
   std::vector<Phase> ph;
+  // Rows per consumer task (1, 2 or 4) of a phase.  A CTA owns only 14-84 rows of a phase; its tasks go
+  // round-robin over the consumer warps, so the phase takes `rounds` x (time of one task), and a task of
+  // NR rows costs about NR + x_cost (the NR rows share each load of the input vector; fp32 rows are
+  // bound by shared-memory loads: x_cost 1, int8 rows by their arithmetic: x_cost 0.5).  Pick the
+  // cheapest; ties go to the fatter task.  KLLM_TASK_ROWS_RT=1|2|4 forces one size for every phase.
+  int forced_task_rows = 0;
+  if (const char* e = getenv("KLLM_TASK_ROWS_RT")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) forced_task_rows = v;
+  }
+  auto pick_task_rows = [&](Phase& p) {
+    const int rpu = p.swiglu ? 2 : 1;
+    p.task_rows = 4;
+    if (p.chunks_per_row != 1) return;
+    if (forced_task_rows) {
+      p.task_rows = std::max(forced_task_rows, rpu);
+      return;
+    }
+    const int rows_cta = ((p.units + grid_ - 1) / grid_) * rpu;
+    const int rps = std::max(rpu, p.rows_per_stage);
+    const double x_cost = int8 ? 0.5 : 1.0;
+    double best_cost = 1e30;
+    for (int nr : {4, 2, 1}) {
+      if (nr < rpu) continue;  // SwiGLU units are row pairs
+      int tasks = 0;
+      for (int left = rows_cta; left > 0; left -= rps) tasks += (std::min(rps, left) + nr - 1) / nr;
+      const int rounds = (tasks + consumer_warps_ - 1) / consumer_warps_;
+      const double cost = rounds * (std::min(nr, rps) + x_cost);
+      if (cost < best_cost - 1e-9) best_cost = cost, p.task_rows = nr;
+    }
+  };
   auto plan = [&](Phase& p) -> int {
     const int row_bytes = p.in_dim * wb;
     p.group_size = m.group_size;
@@ -2481,6 +2544,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       p.rows_per_stage = 1;
       p.scale_off = 0;
     }
+    pick_task_rows(p);
     return 0;
   };
 

@@ -45,6 +45,7 @@ struct Phase {
   int residual_from_emb;  // residual source is the embedding row (layer 0)
   int group_size, group_shift;
   int rows_per_stage;     // whole rows per ring stage (chunks_per_row == 1)
+  int task_rows;          // rows handed to one consumer warp at a time (1, 2 or 4; picked per phase at init)
   int chunks_per_row;     // > 1: a row spans this many stages (fp32 rows longer than a stage)
   int chunk_elems;
   int scale_off;          // byte offset of the scales region inside a stage (int8)
