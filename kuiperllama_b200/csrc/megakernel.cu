@@ -173,15 +173,15 @@ __device__ __forceinline__ float val_of(unsigned long long w) { return __uint_as
 // consumed use n.  A newer tag is therefore a protocol error and traps at once; a word that never
 // turns up becomes a trap after a bounded spin, not a hang.
 __device__ __noinline__ void poll_failed(unsigned seen, unsigned want, long long t_start, int what) {
-  const char* names[3] = {"hand-off word", "residual exchange", "phase input"};
+  const char* name = what == 0 ? "hand-off word" : (what == 1 ? "residual exchange" : "phase input");
   if (static_cast<int>(seen - want) > 0) {
     printf("kllm mega: cta %d thread %d: %s carries tag %u, newer than the awaited %u (protocol error)\n",
-           blockIdx.x, threadIdx.x, names[what], seen, want);
+           blockIdx.x, threadIdx.x, name, seen, want);
     __trap();
   }
   if (clock64() - t_start > kSpinLimit) {
     printf("kllm mega: cta %d thread %d timed out on %s tag %u (last seen %u)\n", blockIdx.x, threadIdx.x,
-           names[what], want, seen);
+           name, want, seen);
     __trap();
   }
 }
@@ -661,6 +661,92 @@ template <int UP>
 __device__ KLLM_STAGE_CALL void stage_handoff(const unsigned long long* src, unsigned tag, int n4, int t, int NT,
                                               float4* xs4);
 
+// ---- inputs of an attention CTA: q (this head), raw k and v (its kv head) of the current position ------------
+// Thread i < hs/2 needs its pair of q (and, in the CTA that handles the new key row, of k); thread d < hs the
+// value element d.  With tagged hand-offs these are up to five words per thread; polled one after the other
+// (each poll a spin loop of its own) they cost five dependent L2 round trips at the head of the layer's
+// critical path -- here all of a thread's words are in flight together and re-read together until every tag is
+// current.  Slots a thread does not need alias a word it does need.
+struct AttnIn {
+  float q0, q1, k0, k1, v;
+};
+__device__ __forceinline__ AttnIn poll_attention_inputs(const unsigned long long* pq0, const unsigned long long* pq1,
+                                                        const unsigned long long* pk0, const unsigned long long* pk1,
+                                                        const unsigned long long* pv, unsigned tag) {
+  unsigned long long w[5];
+  w[0] = ld_tagged_gpu(pq0), w[1] = ld_tagged_gpu(pq1), w[2] = ld_tagged_gpu(pk0), w[3] = ld_tagged_gpu(pk1);
+  w[4] = ld_tagged_gpu(pv);
+  // (no dynamic index into w[]: that would put the buffer into local memory)
+  unsigned seen = tag;
+  auto stale = [&]() -> bool {
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+      if (tag_of(w[i]) != tag) bad = true, seen = tag_of(w[i]);
+    return bad;
+  };
+  if (stale()) {
+    const long long t0 = clock64();
+    do {
+      poll_failed(seen, tag, t0, 0);
+      w[0] = ld_tagged_gpu(pq0), w[1] = ld_tagged_gpu(pq1), w[2] = ld_tagged_gpu(pk0), w[3] = ld_tagged_gpu(pk1);
+      w[4] = ld_tagged_gpu(pv);
+    } while (stale());
+  }
+  return AttnIn{val_of(w[0]), val_of(w[1]), val_of(w[2]), val_of(w[3]), val_of(w[4])};
+}
+
+// RoPE on q (this head) and -- with_k -- on the new key row (rope_kernel.cu as compiled, elementwise.cu); the
+// rotated key goes to k_s and, by one CTA per kv head, into the cache row of `pos`.  Returns this thread's
+// element of the value row (with_v, tid < hs), else 0.  `v_plain`: where thread tid reads its value element when
+// the hand-offs are not tagged.
+__device__ __forceinline__ float attention_inputs(const Params& P, const Phase& ph, int head, int kvh, int pos, unsigned tag_in,
+                                                  bool with_k, bool with_v, float* q_s, float* k_s, float* kcache,
+                                                  const float* v_plain) {
+  const int tid = threadIdx.x;
+  const int hs = P.head_size, seq_len = P.seq_len;
+  const bool handoff = ph.tq != nullptr;  // q / k / v arrive as tagged words: no barrier before us
+  const bool need_q = tid < hs / 2, need_k = need_q && with_k, need_v = with_v && tid < hs;
+  if (!need_q && !need_v) return 0.f;
+  int i0, i1;
+  if (P.flavour == KLLM_FLAVOUR_LLAMA2) {
+    i0 = 2 * tid, i1 = 2 * tid + 1;
+  } else {
+    i0 = tid, i1 = tid + hs / 2;
+  }
+  AttnIn in{0.f, 0.f, 0.f, 0.f, 0.f};
+  if (handoff) {
+    const unsigned long long* pv = ph.tv + kvh * hs + tid;
+    const unsigned long long* pq0 = ph.tq + head * hs + i0;
+    const unsigned long long* pq1 = ph.tq + head * hs + i1;
+    const unsigned long long* any = need_q ? pq0 : pv;  // a word this thread waits for anyway
+    in = poll_attention_inputs(need_q ? pq0 : any, need_q ? pq1 : any, need_k ? ph.tk + kvh * hs + i0 : any,
+                               need_k ? ph.tk + kvh * hs + i1 : any, need_v ? pv : any, tag_in);
+  } else {
+    if (need_q) in.q0 = __ldcg(P.q + static_cast<size_t>(head) * hs + i0), in.q1 = __ldcg(P.q + static_cast<size_t>(head) * hs + i1);
+    if (need_k) in.k0 = __ldcg(P.k_raw + kvh * hs + i0), in.k1 = __ldcg(P.k_raw + kvh * hs + i1);
+    if (need_v) in.v = __ldcg(v_plain);
+  }
+  if (need_q) {
+    const int ci = 2 * tid;
+    const float fci = P.sin_cache[static_cast<size_t>(pos) * hs + ci];
+    const float fcr = P.cos_cache[static_cast<size_t>(pos) * hs + ci];
+    q_s[i0] = __fmaf_rn(fcr, in.q0, -__fmul_rn(fci, in.q1));
+    q_s[i1] = __fmaf_rn(fci, in.q0, __fmul_rn(fcr, in.q1));
+    if (need_k) {
+      const float r0 = __fmaf_rn(fcr, in.k0, -__fmul_rn(fci, in.k1));
+      const float r1 = __fmaf_rn(fci, in.k0, __fmul_rn(fcr, in.k1));
+      k_s[i0] = r0;
+      k_s[i1] = r1;
+      if (head % P.kv_mul == 0) {  // one writer per kv head stores the rotated key
+        kcache[(static_cast<size_t>(i0 >> 2) * seq_len + pos) * 4 + (i0 & 3)] = r0;
+        kcache[(static_cast<size_t>(i1 >> 2) * seq_len + pos) * 4 + (i1 & 3)] = r1;
+      }
+    }
+  }
+  return need_v ? in.v : 0.f;
+}
+
 // ---- attention: SP CTAs per query head, two phases (mha_kernel.cu:47-110 + rope_kernel.cu) ---------
 // The reference gives a head one CTA and so did round 1: 32 of 148 SMs worked while the rest polled,
 // and the time grew with the context.  Every score (one left-to-right FFMA chain per timestep) and
@@ -768,40 +854,9 @@ __device__ KLLM_PHASE_CALL Pipe attention_fused_phase(const Params& P, int head,
   const bool score_in_smem = pos + 1 <= smem_cap;
   float* score_head = score_in_smem ? (ws + 2 * hs) : (P.score + static_cast<size_t>(head) * seq_len);
 
-  // value row of the current position (written by the QKV phase of this token)
-  const bool handoff = ph.tq != nullptr;  // q / k / v arrive as tagged words: no barrier before us
-  float v_pos = 0.f;
-  if (tid < hs)
-    v_pos = handoff ? poll_tagged(ph.tv + kvh * hs + tid, tag_in) : __ldcg(vcache + static_cast<size_t>(pos) * hs + tid);
-
-  // RoPE on q (this head) and on the new key row, rope_kernel.cu as compiled (elementwise.cu)
-  if (tid < hs / 2) {
-    const float* qg = P.q + static_cast<size_t>(head) * hs;
-    const float* kg = P.k_raw + kvh * hs;
-    int i0, i1;
-    if (P.flavour == KLLM_FLAVOUR_LLAMA2) {
-      i0 = 2 * tid, i1 = 2 * tid + 1;
-    } else {
-      i0 = tid, i1 = tid + hs / 2;
-    }
-    const int ci = 2 * tid;
-    const float fci = P.sin_cache[static_cast<size_t>(pos) * hs + ci];
-    const float fcr = P.cos_cache[static_cast<size_t>(pos) * hs + ci];
-    const float q0 = handoff ? poll_tagged(ph.tq + head * hs + i0, tag_in) : __ldcg(qg + i0);
-    const float q1 = handoff ? poll_tagged(ph.tq + head * hs + i1, tag_in) : __ldcg(qg + i1);
-    q_s[i0] = __fmaf_rn(fcr, q0, -__fmul_rn(fci, q1));
-    q_s[i1] = __fmaf_rn(fci, q0, __fmul_rn(fcr, q1));
-    const float k0 = handoff ? poll_tagged(ph.tk + kvh * hs + i0, tag_in) : __ldcg(kg + i0);
-    const float k1 = handoff ? poll_tagged(ph.tk + kvh * hs + i1, tag_in) : __ldcg(kg + i1);
-    const float r0 = __fmaf_rn(fcr, k0, -__fmul_rn(fci, k1));
-    const float r1 = __fmaf_rn(fci, k0, __fmul_rn(fcr, k1));
-    k_s[i0] = r0;
-    k_s[i1] = r1;
-    if (head % P.kv_mul == 0) {  // one writer per kv head stores the rotated key
-      kcache[(static_cast<size_t>(i0 >> 2) * seq_len + pos) * 4 + (i0 & 3)] = r0;
-      kcache[(static_cast<size_t>(i1 >> 2) * seq_len + pos) * 4 + (i1 & 3)] = r1;
-    }
-  }
+  // q, the new key row (rotated) and the value row of the current position (QKV phase of this token)
+  const float v_pos = attention_inputs(P, ph, head, kvh, pos, tag_in, true, true, q_s, k_s, kcache,
+                                       vcache + static_cast<size_t>(pos) * hs + tid);
   consumer_sync<CT>();
   const long long c_rope = stamp ? clock64() : 0;
 
@@ -973,38 +1028,8 @@ __device__ KLLM_PHASE_CALL Pipe attention_scores_phase(const Params& P, int head
   const size_t head_block = (static_cast<size_t>(ph.layer) * (P.kv_dim / hs) + kvh) * seq_len * hs;
   float* kcache = P.key_cache + head_block;
   unsigned long long* sc_out = P.scores + static_cast<size_t>(head) * seq_len;
-  const bool handoff = ph.tq != nullptr;  // q / k arrive as tagged words: no barrier before us
-
-  // RoPE on q (this head) and on the new key row, rope_kernel.cu as compiled (elementwise.cu)
-  if (tid < hs / 2) {
-    const float* qg = P.q + static_cast<size_t>(head) * hs;
-    const float* kg = P.k_raw + kvh * hs;
-    int i0, i1;
-    if (P.flavour == KLLM_FLAVOUR_LLAMA2) {
-      i0 = 2 * tid, i1 = 2 * tid + 1;
-    } else {
-      i0 = tid, i1 = tid + hs / 2;
-    }
-    const int ci = 2 * tid;
-    const float fci = P.sin_cache[static_cast<size_t>(pos) * hs + ci];
-    const float fcr = P.cos_cache[static_cast<size_t>(pos) * hs + ci];
-    const float q0 = handoff ? poll_tagged(ph.tq + head * hs + i0, tag_in) : __ldcg(qg + i0);
-    const float q1 = handoff ? poll_tagged(ph.tq + head * hs + i1, tag_in) : __ldcg(qg + i1);
-    q_s[i0] = __fmaf_rn(fcr, q0, -__fmul_rn(fci, q1));
-    q_s[i1] = __fmaf_rn(fci, q0, __fmul_rn(fcr, q1));
-    if (split == 0) {  // the new key row: one CTA of the head scores it, one CTA per kv head stores it
-      const float k0 = handoff ? poll_tagged(ph.tk + kvh * hs + i0, tag_in) : __ldcg(kg + i0);
-      const float k1 = handoff ? poll_tagged(ph.tk + kvh * hs + i1, tag_in) : __ldcg(kg + i1);
-      const float r0 = __fmaf_rn(fcr, k0, -__fmul_rn(fci, k1));
-      const float r1 = __fmaf_rn(fci, k0, __fmul_rn(fcr, k1));
-      k_s[i0] = r0;
-      k_s[i1] = r1;
-      if (head % P.kv_mul == 0) {
-        kcache[(static_cast<size_t>(i0 >> 2) * seq_len + pos) * 4 + (i0 & 3)] = r0;
-        kcache[(static_cast<size_t>(i1 >> 2) * seq_len + pos) * 4 + (i1 & 3)] = r1;
-      }
-    }
-  }
+  // q and -- in the CTA that scores it -- the new key row, rotated (the value row is the P.V phase's business)
+  attention_inputs(P, ph, head, kvh, pos, tag_in, split == 0, false, q_s, k_s, kcache, nullptr);
   consumer_sync<CT>();
   const long long c_rope = stamp ? clock64() : 0;
 
@@ -1242,41 +1267,9 @@ __device__ KLLM_PHASE_CALL Pipe attention_flash_phase(const Params& P, int head,
   const int kvh = head / P.kv_mul;
   const size_t head_block = (static_cast<size_t>(ph.layer) * (P.kv_dim / hs) + kvh) * seq_len * hs;
   float* kcache = P.key_cache + head_block;
-  const bool handoff = ph.tq != nullptr;  // q / k / v arrive as tagged words: no barrier before us
-
-  float v_pos = 0.f;  // the value row of the current position (CTA 0 of the head)
-  if (split == 0 && tid < hs)
-    v_pos = handoff ? poll_tagged(ph.tv + kvh * hs + tid, tag_in)
-                    : __ldcg(P.value_cache + head_block + static_cast<size_t>(pos) * hs + tid);
-  if (tid < hs / 2) {  // RoPE on q (this head) and on the new key row (rope_kernel.cu as compiled)
-    const float* qg = P.q + static_cast<size_t>(head) * hs;
-    const float* kg = P.k_raw + kvh * hs;
-    int i0, i1;
-    if (P.flavour == KLLM_FLAVOUR_LLAMA2) {
-      i0 = 2 * tid, i1 = 2 * tid + 1;
-    } else {
-      i0 = tid, i1 = tid + hs / 2;
-    }
-    const int ci = 2 * tid;
-    const float fci = P.sin_cache[static_cast<size_t>(pos) * hs + ci];
-    const float fcr = P.cos_cache[static_cast<size_t>(pos) * hs + ci];
-    const float q0 = handoff ? poll_tagged(ph.tq + head * hs + i0, tag_in) : __ldcg(qg + i0);
-    const float q1 = handoff ? poll_tagged(ph.tq + head * hs + i1, tag_in) : __ldcg(qg + i1);
-    q_s[i0] = __fmaf_rn(fcr, q0, -__fmul_rn(fci, q1));
-    q_s[i1] = __fmaf_rn(fci, q0, __fmul_rn(fcr, q1));
-    if (split == 0) {
-      const float k0 = handoff ? poll_tagged(ph.tk + kvh * hs + i0, tag_in) : __ldcg(kg + i0);
-      const float k1 = handoff ? poll_tagged(ph.tk + kvh * hs + i1, tag_in) : __ldcg(kg + i1);
-      const float r0 = __fmaf_rn(fcr, k0, -__fmul_rn(fci, k1));
-      const float r1 = __fmaf_rn(fci, k0, __fmul_rn(fcr, k1));
-      k_s[i0] = r0;
-      k_s[i1] = r1;
-      if (head % P.kv_mul == 0) {  // one writer per kv head stores the rotated key
-        kcache[(static_cast<size_t>(i0 >> 2) * seq_len + pos) * 4 + (i0 & 3)] = r0;
-        kcache[(static_cast<size_t>(i1 >> 2) * seq_len + pos) * 4 + (i1 & 3)] = r1;
-      }
-    }
-  }
+  // q, and in CTA 0 of the head the new key row (rotated) and the value row of the current position
+  const float v_pos = attention_inputs(P, ph, head, kvh, pos, tag_in, split == 0, split == 0, q_s, k_s, kcache,
+                                       P.value_cache + head_block + static_cast<size_t>(pos) * hs + tid);
   consumer_sync<CT>();
   const long long c_rope = stamp ? clock64() : 0;
 
@@ -1404,23 +1397,41 @@ __device__ KLLM_PHASE_CALL Pipe attention_flash_phase(const Params& P, int head,
       if (tid == 0) st_tagged2_gpu(mine, M, den, tag_out);
     } else {
       const int active = min(SP, n_tiles);  // CTAs 1 .. active - 1 of the head had tiles
-      for (int sidx = 1; sidx < active; ++sidx) {
-        const unsigned long long* theirs = area + static_cast<size_t>(sidx) * (hs + 2);
-        unsigned long long w_m, w_l, w_o;
+      // their partials, up to three CTAs' (m, l, o[tid]) in flight together: polled one CTA after the other
+      // every partial would be another L2 round trip on the layer's critical path
+      for (int s0 = 1; s0 < active; s0 += 3) {
+        unsigned long long w_m[3], w_l[3], w_o[3];
+        const int ns = min(3, active - s0);
         const long long t_start = clock64();
-        for (;;) {  // the three words in flight together
-          ld_tagged2_gpu(theirs, w_m, w_l);
-          w_o = ld_tagged_gpu(theirs + 2 + tid);
-          if (tag_of(w_m) == tag_out && tag_of(w_l) == tag_out && tag_of(w_o) == tag_out) break;
-          const unsigned seen = tag_of(w_o) != tag_out ? tag_of(w_o) : (tag_of(w_m) != tag_out ? tag_of(w_m) : tag_of(w_l));
+        for (;;) {
+          bool ok = true;
+          unsigned seen = tag_out;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const unsigned long long* theirs = area + static_cast<size_t>(s0 + min(k, ns - 1)) * (hs + 2);
+            ld_tagged2_gpu(theirs, w_m[k], w_l[k]);
+            w_o[k] = ld_tagged_gpu(theirs + 2 + tid);
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            if (tag_of(w_m[k]) != tag_out) ok = false, seen = tag_of(w_m[k]);
+            if (tag_of(w_l[k]) != tag_out) ok = false, seen = tag_of(w_l[k]);
+            if (tag_of(w_o[k]) != tag_out) ok = false, seen = tag_of(w_o[k]);
+          }
+          if (ok) break;
           poll_failed(seen, tag_out, t_start, 0);
         }
-        const float ms = val_of(w_m), ls = val_of(w_l), os = val_of(w_o);
-        const float M_new = fmaxf(M, ms);
-        const float fa = expf(M - M_new), fb = expf(ms - M_new);
-        num = __fmaf_rn(num, fa, os * fb);
-        den = __fmaf_rn(den, fa, ls * fb);
-        M = M_new;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          if (k < ns) {  // in CTA order, as before
+            const float ms = val_of(w_m[k]), ls = val_of(w_l[k]), os = val_of(w_o[k]);
+            const float M_new = fmaxf(M, ms);
+            const float fa = expf(M - M_new), fb = expf(ms - M_new);
+            num = __fmaf_rn(num, fa, os * fb);
+            den = __fmaf_rn(den, fa, ls * fb);
+            M = M_new;
+          }
+        }
       }
       const float value = num / den;
       if (ph.ta != nullptr)
@@ -2383,9 +2394,12 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
     for (int d : dims)
       if (d % m.group_size != 0 || ((d / m.group_size) * 4) % 16 != 0) return KLLM_E_UNSUPPORTED;
   }
-  // consumer warps: int8 rows are bound by instruction issue (4 instructions per weight byte), so
-  // they get 16 warps of <= 112 registers; fp32 rows by shared-memory bandwidth, 8 fat warps
-  consumer_warps_ = int8 ? 16 : 6;
+  // consumer warps (+ the ring producer and the L2 prefetcher): fp32 rows 8 x 168 registers; int8 rows are
+  // bound by instruction issue and want many warps -- 14, so that the CTA is 16 warps = 4 per scheduler with
+  // 128 registers each (16 consumers make 18 warps, which caps them at 96 registers and spills).  Measured on
+  // B200 (profiles/README.md, pass Q): fp32 6 vs 8 warps 1072 = 1072 (TinyLlama), 1218 < 1296 (Qwen2.5-0.5B),
+  // 210 < 213 (Llama-2-7B); int8 16 / 14 / 8 warps 394 / 400 / 375 tok/s.
+  consumer_warps_ = int8 ? 14 : 8;
   if (const char* e = getenv("KLLM_CONSUMER_WARPS")) {
     const int v = atoi(e);
     if (int8 && (v == 6 || v == 8 || v == 14 || v == 16)) consumer_warps_ = v;  // fast mode: CT >= 192 quantises M <= 16384 in <= 6 rounds
@@ -2501,7 +2515,9 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       if (nr < rpu) continue;  // SwiGLU units are row pairs
       int tasks = 0;
       for (int left = rows_cta; left > 0; left -= rps) tasks += (std::min(rps, left) + nr - 1) / nr;
-      const int rounds = (tasks + consumer_warps_ - 1) / consumer_warps_;
+      // tasks never cross a ring stage, so at most stages x (tasks per stage) of them exist at a time
+      const int concurrent = std::max(1, std::min(consumer_warps_, stages * ((rps + nr - 1) / nr)));
+      const int rounds = (tasks + concurrent - 1) / concurrent;
       const double cost = rounds * (std::min(nr, rps) + x_cost);
       if (cost < best_cost - 1e-9) best_cost = cost, p.task_rows = nr;
     }
@@ -2852,7 +2868,9 @@ int MegaEngine::run(int n_tokens, const int32_t* teacher_dev, unsigned long long
   P.attn_vsplit = attn_vsplit_;
   P.attn_parts = attn_parts_;
   P.scores = d_scores_;
-  P.pf_stages = 8;  // 8 x 32 KB x 148 SMs = 38 MB of weights in flight towards L2 (measured: 6-12 best, >=24 thrashes L2)
+  // 256 KB per SM = 38 MB of weights in flight towards L2 chip-wide (measured with 32 KB stages: 6-12 stages
+  // best, >= 24 thrashes L2); in stages, so that a smaller stage size keeps the same byte distance
+  P.pf_stages = std::max(4, (256 * 1024) / std::max(1, stage_bytes_));
   if (const char* e = getenv("KLLM_PREFETCH_STAGES")) P.pf_stages = std::max(0, atoi(e));
   P.group_size = m.group_size;
   P.dim = m.dim;

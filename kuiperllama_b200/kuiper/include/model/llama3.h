@@ -19,8 +19,10 @@
 #include <vector>
 
 #include "model.h"
+#include "tensor_parallel.h"
 
 struct kllm_decoder;  // include/kllm_b200.h
+struct kllm_comm;
 
 namespace model {
 // Every operator instance of the model.  The *_layers_ vectors hold one entry per transformer
@@ -57,6 +59,15 @@ class LLama2Model : public Model {
   // "persistent" / "graph": which engine the fused decoder picked (diagnostic)
   const char* decoder_engine() const;
 
+  // Tensor parallelism (model/tensor_parallel.h): call before init(); without a call init() takes the
+  // configuration from the KUIPER_TP_* environment (set by tools/kuiper_tp_launch), so the reference's
+  // unchanged demo programs run sharded under the launcher.  One process per GPU; this process loads
+  // only its shard of every layer matrix, and predict() is the only per-token path (forward() is the
+  // single-GPU layer-by-layer path and refuses to run on a shard).
+  void set_tensor_parallel(const TpConfig& config);
+  const TpConfig& tensor_parallel() const { return tp_; }
+  const TpShard& tensor_parallel_shard() const { return shard_; }
+
  protected:
   // qkv_bias: the checkpoint carries a bias vector behind each layer's wq / wk / wv (Qwen2 files)
   LLama2Model(base::TokenizerType tokenizer_type, std::string token_path, std::string model_path,
@@ -73,6 +84,7 @@ class LLama2Model : public Model {
   int32_t post_processing(const tensor::Tensor& pos, bool is_prompt) const override;
 
   base::Status create_decoder();
+  base::Status connect_ranks();
   void ensure_lazy_buffer(ModelBufferType buffer_idx) const;
 
   // the stages of forward(), one transformer layer at a time
@@ -95,6 +107,15 @@ class LLama2Model : public Model {
   mutable int32_t decoder_rows_ = 0;
   mutable int32_t layer_rows_ = 0;
   base::Status sync_layer_cache(int32_t pos) const;
+
+  // tensor parallel state: who we are, what we own, the exchange and the start-up rendezvous; the host
+  // staging buffers of the repacked column shards live until init_mem() has uploaded them
+  TpConfig tp_;
+  bool tp_explicit_ = false;
+  TpShard shard_;
+  kllm_comm* comm_ = nullptr;
+  std::unique_ptr<TpRendezvous> rendezvous_;
+  std::vector<std::shared_ptr<base::Buffer>> tp_staging_;
 };
 }  // namespace model
 #endif  // KLLM_KUIPER_MODEL_LLAMA3_H_

@@ -20,6 +20,7 @@
 #include <op/mha.h>
 #include <op/rmsnorm.h>
 
+#include <cstring>
 #include <utility>
 
 #include "../op/kernels/kernels_interface.h"
@@ -56,7 +57,18 @@ LLama2Model::LLama2Model(base::TokenizerType tokenizer_type, std::string token_p
       qkv_bias_(qkv_bias) {}
 
 LLama2Model::~LLama2Model() {
+  if (comm_ != nullptr) {
+    // nobody frees its exchange area while a peer's kernel may still push into it
+    cudaDeviceSynchronize();
+    if (rendezvous_ && rendezvous_->is_open()) rendezvous_->barrier();
+  }
   if (decoder_ != nullptr) kllm_decoder_destroy(decoder_);
+  if (comm_ != nullptr) kllm_comm_destroy(comm_);
+}
+
+void LLama2Model::set_tensor_parallel(const TpConfig& config) {
+  tp_ = config;
+  tp_explicit_ = true;
 }
 
 const char* LLama2Model::decoder_engine() const { return decoder_ ? kllm_decoder_engine(decoder_) : ""; }
@@ -69,7 +81,10 @@ base::Status LLama2Model::init(base::DeviceType device_type) {
         "This library is the B200 (sm_100a) backend: init(kDeviceCUDA) is the only supported device; it has "
         "no CPU path.");
   device_type_ = device_type;
-  if (cudaSetDevice(0) != cudaSuccess) return error::InternalError("No usable CUDA device.");
+  if (!tp_explicit_) tp_ = TpConfig::from_env();  // tools/kuiper_tp_launch: one process per GPU
+  if (tp_.rank < 0 || tp_.rank >= tp_.world) return error::InvalidArgument("tensor parallel: rank outside the world");
+  if (cudaSetDevice(tp_.cuda_device()) != cudaSuccess)
+    return error::InternalError("No usable CUDA device " + std::to_string(tp_.cuda_device()) + ".");
   cuda_config_ = std::make_shared<kernel::CudaConfig>();
   if (cudaStreamCreate(&cuda_config_->stream) != cudaSuccess)
     return error::InternalError("The cuda handle create failed.");
@@ -103,19 +118,36 @@ void LLama2Model::create_param_layers() {
   const auto cpu = base::DeviceType::kDeviceCPU;
   const int32_t dim = config_->dim_, kvd = config_->kv_dim_, hid = config_->hidden_dim_;
   const int32_t L = config_->layer_num_, V = config_->vocab_size_;
+  const bool tp = tp_.on();
   size_t off = 0;  // in floats
   auto take = [&](size_t n) {
     const void* p = raw_model_data_->weight(off);
     off += n;
     return p;
   };
-  auto matmul_group = [&](std::vector<std::shared_ptr<op::Layer>>& dst, int32_t rows, int32_t cols, bool bias) {
+  // One [rows, cols] matrix per layer; under tensor parallelism only rows [r0, r1) (a contiguous span of
+  // the file, viewed in place) or columns [c0, c1) (packed once into a host staging buffer) are kept.
+  auto matmul_group = [&](std::vector<std::shared_ptr<op::Layer>>& dst, int32_t rows, int32_t cols, bool bias,
+                          int32_t r0, int32_t r1, int32_t c0, int32_t c1) {
+    const int32_t lr = r1 - r0, lc = c1 - c0;
     for (int32_t i = 0; i < L; ++i) {
-      auto m = std::make_shared<op::MatmulLayer>(device_type_, rows, cols, false, bias);
-      m->set_weight(0, {rows, cols}, take(static_cast<size_t>(rows) * cols), cpu);
+      auto m = std::make_shared<op::MatmulLayer>(device_type_, lr, lc, false, bias);
+      const float* full = static_cast<const float*>(take(static_cast<size_t>(rows) * cols));
+      if (lc == cols) {
+        m->set_weight(0, {lr, lc}, full + static_cast<size_t>(r0) * cols, cpu);
+      } else {
+        auto pack = std::make_shared<base::Buffer>(static_cast<size_t>(lr) * lc * sizeof(float),
+                                                   base::CPUDeviceAllocatorFactory::get_instance());
+        float* p = static_cast<float*>(pack->ptr());
+        for (int32_t r = 0; r < lr; ++r)
+          std::memcpy(p + static_cast<size_t>(r) * lc, full + static_cast<size_t>(r0 + r) * cols + c0,
+                      static_cast<size_t>(lc) * sizeof(float));
+        m->set_weight(0, {lr, lc}, p, cpu);
+        tp_staging_.push_back(std::move(pack));
+      }
       if (bias) {
-        int32_t n = rows;
-        m->set_bias(0, n, take(rows), cpu);
+        int32_t n = lr;
+        m->set_bias(0, n, static_cast<const float*>(take(rows)) + r0, cpu);
       }
       dst.push_back(m);
     }
@@ -127,6 +159,9 @@ void LLama2Model::create_param_layers() {
       llama_layers_->rmsnorm_layers_.push_back(n);
     }
   };
+  const TpShard& sh = shard_;
+  const int32_t q0 = tp ? sh.q0 : 0, q1 = tp ? sh.q1 : dim, k0 = tp ? sh.k0 : 0, k1 = tp ? sh.k1 : kvd;
+  const int32_t f0 = tp ? sh.f0 : 0, f1 = tp ? sh.f1 : hid;
 
   auto emb = std::make_shared<op::EmbeddingLayer>(device_type_, dim, config_->seq_len_, V);
   const void* emb_ptr = take(static_cast<size_t>(V) * dim);
@@ -134,14 +169,14 @@ void LLama2Model::create_param_layers() {
   llama_layers_->embedding_layer_ = emb;
 
   norm_group(L);  // attention norms -> rmsnorm_layers_[0, L)
-  matmul_group(llama_layers_->wq_layers_, dim, dim, qkv_bias_);
-  matmul_group(llama_layers_->wk_layers_, kvd, dim, qkv_bias_);
-  matmul_group(llama_layers_->wv_layers_, kvd, dim, qkv_bias_);
-  matmul_group(llama_layers_->wo_layers_, dim, dim, false);
+  matmul_group(llama_layers_->wq_layers_, dim, dim, qkv_bias_, q0, q1, 0, dim);
+  matmul_group(llama_layers_->wk_layers_, kvd, dim, qkv_bias_, k0, k1, 0, dim);
+  matmul_group(llama_layers_->wv_layers_, kvd, dim, qkv_bias_, k0, k1, 0, dim);
+  matmul_group(llama_layers_->wo_layers_, dim, dim, false, 0, dim, q0, q1);
   norm_group(L);  // ffn norms -> [L, 2L)
-  matmul_group(llama_layers_->w1_layers_, hid, dim, false);
-  matmul_group(llama_layers_->w2_layers_, dim, hid, false);
-  matmul_group(llama_layers_->w3_layers_, hid, dim, false);
+  matmul_group(llama_layers_->w1_layers_, hid, dim, false, f0, f1, 0, dim);
+  matmul_group(llama_layers_->w2_layers_, dim, hid, false, 0, dim, f0, f1);
+  matmul_group(llama_layers_->w3_layers_, hid, dim, false, f0, f1, 0, dim);
   norm_group(1);  // final norm -> [2L]
   take(static_cast<size_t>(config_->seq_len_) * config_->head_size_);  // freqs_cos + freqs_sin: unused
 
@@ -157,29 +192,70 @@ void LLama2Model::create_param_quant_layers() {
   const auto cpu = base::DeviceType::kDeviceCPU;
   const int32_t dim = config_->dim_, kvd = config_->kv_dim_, hid = config_->hidden_dim_;
   const int32_t L = config_->layer_num_, V = config_->vocab_size_;
+  const int32_t g = group_size_;
+  const bool tp = tp_.on();
   size_t off = 0;  // in bytes
-  auto quant_matmul = [&](int32_t rows, int32_t cols) {
-    auto m = std::make_shared<op::MatmulLayer>(device_type_, rows, cols, true);
-    m->set_group_size(group_size_);
-    m->set_weight(0, {rows, cols}, raw_model_data_->weight(off), cpu);
-    off += static_cast<size_t>(rows) * cols + static_cast<size_t>(m->get_scale_num()) * sizeof(float);
+  // One tensor of the file: int8 [rows, cols] followed by its fp32 scales [rows * cols / g].  Under tensor
+  // parallelism rows [r0, r1) keep viewing the file (the weight slice and the scale slice are two
+  // contiguous spans); columns [c0, c1) -- c0, c1 multiples of g -- are packed into host staging buffers.
+  auto quant_matmul = [&](int32_t rows, int32_t cols, int32_t r0, int32_t r1, int32_t c0, int32_t c1) {
+    const int32_t lr = r1 - r0, lc = c1 - c0;
+    auto m = std::make_shared<op::MatmulLayer>(device_type_, lr, lc, true);
+    m->set_group_size(g);
+    const int8_t* full = static_cast<const int8_t*>(raw_model_data_->weight(off));
+    const size_t numel = static_cast<size_t>(rows) * cols;
+    const float* full_scales = reinterpret_cast<const float*>(full + numel);
+    off += numel + numel / g * sizeof(float);
+    if (lr == rows && lc == cols) {
+      m->set_weight(0, {rows, cols}, full, cpu);  // scales: right behind the block
+      return m;
+    }
+    CHECK(cols % g == 0 && c0 % g == 0 && lc % g == 0) << "quantisation groups straddle the shard";
+    const size_t n_scales = static_cast<size_t>(lr) * lc / g;
+    const int8_t* w_ptr;
+    const float* s_ptr;
+    if (lc == cols) {
+      w_ptr = full + static_cast<size_t>(r0) * cols;
+      s_ptr = full_scales + static_cast<size_t>(r0) * cols / g;
+    } else {
+      auto pack = std::make_shared<base::Buffer>(static_cast<size_t>(lr) * lc + n_scales * sizeof(float),
+                                                 base::CPUDeviceAllocatorFactory::get_instance());
+      int8_t* pw = static_cast<int8_t*>(pack->ptr());
+      float* ps = reinterpret_cast<float*>(pw + static_cast<size_t>(lr) * lc);  // lr * lc % 4 == 0
+      for (int32_t r = 0; r < lr; ++r) {
+        std::memcpy(pw + static_cast<size_t>(r) * lc, full + static_cast<size_t>(r0 + r) * cols + c0, lc);
+        std::memcpy(ps + static_cast<size_t>(r) * (lc / g), full_scales + (static_cast<size_t>(r0 + r) * cols + c0) / g,
+                    static_cast<size_t>(lc / g) * sizeof(float));
+      }
+      w_ptr = pw, s_ptr = ps;
+      tp_staging_.push_back(std::move(pack));
+    }
+    m->set_weight(0, {lr, lc}, w_ptr, cpu);
+    tensor::Tensor scales(base::DataType::kDataTypeFp32, static_cast<int32_t>(n_scales), false, nullptr,
+                          const_cast<float*>(s_ptr));
+    scales.set_device_type(cpu);
+    m->set_scales(scales);
     return m;
   };
-  auto group = [&](std::vector<std::shared_ptr<op::Layer>>& dst, int32_t rows, int32_t cols) {
-    for (int32_t i = 0; i < L; ++i) dst.push_back(quant_matmul(rows, cols));
+  auto group = [&](std::vector<std::shared_ptr<op::Layer>>& dst, int32_t rows, int32_t cols, int32_t r0, int32_t r1,
+                   int32_t c0, int32_t c1) {
+    for (int32_t i = 0; i < L; ++i) dst.push_back(quant_matmul(rows, cols, r0, r1, c0, c1));
   };
-  group(llama_layers_->wq_layers_, dim, dim);
-  group(llama_layers_->wk_layers_, kvd, dim);
-  group(llama_layers_->wv_layers_, kvd, dim);
-  group(llama_layers_->wo_layers_, dim, dim);
-  group(llama_layers_->w1_layers_, hid, dim);
-  group(llama_layers_->w2_layers_, dim, hid);
-  group(llama_layers_->w3_layers_, hid, dim);
+  const TpShard& sh = shard_;
+  const int32_t q0 = tp ? sh.q0 : 0, q1 = tp ? sh.q1 : dim, k0 = tp ? sh.k0 : 0, k1 = tp ? sh.k1 : kvd;
+  const int32_t f0 = tp ? sh.f0 : 0, f1 = tp ? sh.f1 : hid;
+  group(llama_layers_->wq_layers_, dim, dim, q0, q1, 0, dim);
+  group(llama_layers_->wk_layers_, kvd, dim, k0, k1, 0, dim);
+  group(llama_layers_->wv_layers_, kvd, dim, k0, k1, 0, dim);
+  group(llama_layers_->wo_layers_, dim, dim, 0, dim, q0, q1);
+  group(llama_layers_->w1_layers_, hid, dim, f0, f1, 0, dim);
+  group(llama_layers_->w2_layers_, dim, hid, 0, dim, f0, f1);
+  group(llama_layers_->w3_layers_, hid, dim, f0, f1, 0, dim);
   // A shared classifier cannot be expressed in this format: the exporter writes no int8 copy of
   // the embedding and the reference then reads the fp32 table as int8 (llama3.cpp:259-277).
   CHECK(!config_->is_shared_weight_)
       << "int8 checkpoints with a shared classifier are not loadable (reference defect, see DESIGN.md)";
-  llama_layers_->cls_layer_ = quant_matmul(V, dim);
+  llama_layers_->cls_layer_ = quant_matmul(V, dim, 0, V, 0, dim);
 
   const float* f = static_cast<const float*>(raw_model_data_->weight(off));
   auto emb = std::make_shared<op::EmbeddingLayer>(device_type_, dim, config_->seq_len_, V);
@@ -197,6 +273,12 @@ void LLama2Model::create_param_quant_layers() {
 base::Status LLama2Model::create_layers() {
   using namespace base;
   if (!llama_layers_) llama_layers_ = std::make_unique<LLama2Layers>();
+  if (tp_.on()) {
+    if (Status st = tp_shard(*config_, is_quant_model_ ? group_size_ : 0, tp_.world, tp_.rank, &shard_); !st) return st;
+    LOG(INFO) << "tensor parallel rank " << tp_.rank << " of " << tp_.world << ": heads [" << shard_.q0 / config_->head_size_
+              << ", " << shard_.q1 / config_->head_size_ << "), kv rows [" << shard_.k0 << ", " << shard_.k1
+              << "), FFN rows [" << shard_.f0 << ", " << shard_.f1 << ")";
+  }
   // the file must hold exactly what the header promises before any view is taken
   {
     const size_t dim = config_->dim_, kvd = config_->kv_dim_, hid = config_->hidden_dim_, L = config_->layer_num_,
@@ -236,8 +318,9 @@ base::Status LLama2Model::create_layers() {
 void LLama2Model::init_mem() {
   CHECK(device_type_ == base::DeviceType::kDeviceCUDA);
   CHECK_NE(cuda_config_, nullptr);
-  llama_layers_->to_cuda(cuda_config_);  // weights: mmap -> device
+  llama_layers_->to_cuda(cuda_config_);  // weights: mmap (or the packed column shards) -> device
   cudaStreamSynchronize(cuda_config_->stream);
+  tp_staging_.clear();
   // the host mapping is no longer needed for the weights that now live on the device
   auto cpu = base::CPUDeviceAllocatorFactory::get_instance();
   auto gpu = base::CUDADeviceAllocatorFactory::get_instance();
@@ -368,12 +451,46 @@ base::Status LLama2Model::create_decoder() {
     d.bq = bq.data(), d.bk = bk.data(), d.bv = bv.data();
   }
   d.tp_size = 1;
+  if (tp_.on()) {
+    // this rank's shard: LOCAL head / kv-head / FFN counts, full model dim (include/kllm_b200.h)
+    if (base::Status st = connect_ranks(); !st) return st;
+    d.head_num = shard_.head_num, d.kv_head_num = shard_.kv_head_num, d.hidden_dim = shard_.hidden_dim;
+    d.tp_size = tp_.world, d.tp_rank = tp_.rank;
+    d.comm = comm_;
+  }
+  if (const char* mode = std::getenv("KUIPER_NUMERICS"); mode && std::string(mode) == "fast") d.numerics = KLLM_NUMERICS_FAST;
   const int rc = kllm_decoder_create(&d, cuda_config_->stream, &decoder_);
   if (rc != 0)
     return base::error::InternalError(std::string("kllm_decoder_create failed: ") + kllm_error_string(rc));
   LOG(INFO) << "fused decoder engine: " << kllm_decoder_engine(decoder_) << ", "
             << kllm_decoder_launches_per_step(decoder_) << " launch(es) per token";
+  if (tp_.on()) {
+    // every rank has built its engine (and zeroed its exchange area) before anybody's first token
+    cudaDeviceSynchronize();
+    if (base::Status st = rendezvous_->barrier(); !st) return st;
+  }
   return base::error::Success();
+}
+
+// The exchange between the ranks: create this rank's kllm_comm (peer-memory transport), swap the 64-byte
+// CUDA-IPC handles of the exchange areas over the rendezvous, map every peer.  What tensor_parallel.Comm
+// does through torch.distributed on the Python side.
+base::Status LLama2Model::connect_ranks() {
+  using base::error::InternalError;
+  if (comm_ != nullptr) return base::error::Success();
+  rendezvous_ = std::make_unique<TpRendezvous>();
+  if (base::Status st = rendezvous_->open(tp_); !st) return st;
+  int rc = kllm_comm_create(tp_.world, tp_.rank, KLLM_COMM_PEER, tp_comm_words(*config_, tp_.world), nullptr, &comm_);
+  if (rc != 0) return InternalError(std::string("kllm_comm_create: ") + kllm_error_string(rc));
+  unsigned char mine[64] = {0};
+  rc = kllm_comm_ipc_handle(comm_, mine);
+  if (rc != 0) return InternalError(std::string("kllm_comm_ipc_handle: ") + kllm_error_string(rc));
+  std::vector<unsigned char> all(static_cast<size_t>(64) * tp_.world);
+  if (base::Status st = rendezvous_->all_gather(mine, sizeof(mine), all.data()); !st) return st;
+  rc = kllm_comm_connect(comm_, all.data());
+  if (rc != 0) return InternalError(std::string("kllm_comm_connect: ") + kllm_error_string(rc));
+  cudaDeviceSynchronize();
+  return rendezvous_->barrier();  // every rank has mapped every peer before the first exchange
 }
 
 // ---- embedding / predict -----------------------------------------------------------------------------
@@ -418,6 +535,10 @@ base::Status LLama2Model::predict(const tensor::Tensor& input, const tensor::Ten
       return base::error::Success();
     }
   }
+  if (tp_.on())
+    return base::error::InvalidArgument(
+        "tensor parallel: predict() needs a row of the last embedding() call (the fused decoder is the only "
+        "sharded path)");
   base::Status st = forward(input, pos_tensor, next);
   if (!st) return st;
   next = post_processing(pos_tensor, is_prompt);
@@ -447,6 +568,9 @@ base::Status LLama2Model::sync_layer_cache(int32_t pos) const {
 base::Status LLama2Model::forward(const tensor::Tensor& input, const tensor::Tensor& pos_tensor, int& next) const {
   UNUSED(next);
   if (input.is_empty()) return base::error::InvalidArgument("The input tensor is empty.");
+  if (tp_.on())
+    return base::error::FunctionNotImplement("forward() is the single-GPU layer-by-layer path; a tensor-parallel "
+                                             "model steps through predict()");
   const int32_t pos = pos_tensor.index<int32_t>(0);
   if (base::Status st = sync_layer_cache(pos); !st) return st;
   for (int32_t l = 0; l < config_->layer_num_; ++l) {

@@ -106,7 +106,7 @@ int main(int argc, char** argv) {
   }
   for (size_t i = 0; i < chosen.size(); ++i) std::printf("%s%d", i ? " " : "", chosen[i]);
   std::printf("\n");
-  if (!logits_path.empty()) {
+  if (!logits_path.empty() && m->tensor_parallel().rank == 0) {  // under kuiper_tp_launch every rank holds the same logits
     tensor::Tensor lg = m->get_buffer(model::ModelBufferType::kForwardOutput).clone();
     lg.to_cpu();
     FILE* f = std::fopen(logits_path.c_str(), "wb");

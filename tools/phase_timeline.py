@@ -75,6 +75,47 @@ def main():
     print(f"# attention (scores + softmax + P.V) on the first {heads} attention CTAs: median {np.median(attn):.2f} us, slowest head per layer (mean) "
           f"{attn.max(axis=0).mean():.2f} us")
     print(f"# sum of phase durations: {dur.sum():.1f} us; barrier_min = time the LAST arriving CTA spends in the barrier")
+    # ---- critical path: absolute times of one layer's all-to-all points, averaged over the layers -----------
+    # last_done(X) = when the slowest CTA finished producing X; polled(Y) = when the median CTA held all of
+    # Y's input vector; hand-off latency = polled(next) - last_done(prev); the phase body = last_done - polled.
+    n_attn = shape.head_num * sp
+    if NPL == 5:
+        k_qkv, k_attn, k_wo, k_w13, k_w2 = 0, 1, 2, 3, 4
+        rows = []
+        for l in range(1, L - 1):
+            b = l * NPL
+            q_pol = np.median(polled[:, b + k_qkv])
+            q_done = st[:, b + k_qkv, 2].max()
+            a_done = st[:n_attn, b + k_attn, 2].max()
+            a_done_med = np.median(st[:n_attn, b + k_attn, 2])
+            wo_pol = np.median(polled[:, b + k_wo])
+            wo_done = st[:, b + k_wo, 2].max()
+            w13_pol = np.median(polled[:, b + k_w13])
+            w13_done = st[:, b + k_w13, 2].max()
+            w2_pol = np.median(polled[:, b + k_w2])
+            w2_done = st[:, b + k_w2, 2].max()
+            nq_pol = np.median(polled[:, b + NPL + k_qkv])
+            rows.append([q_done - q_pol, a_done_med - q_done, a_done - q_done, wo_pol - a_done, wo_done - wo_pol,
+                         w13_pol - wo_done, w13_done - w13_pol, w2_pol - w13_done, w2_done - w2_pol, nq_pol - w2_done,
+                         nq_pol - q_pol])
+        m = np.array(rows).mean(axis=0)
+        print("# critical path of a layer (us, mean over layers 1..L-2): qkv body %.2f | attention: median CTA done +%.2f, "
+              "last CTA done +%.2f after the last qkv row | -> wo input complete %.2f | wo body %.2f | -> w1w3 input %.2f | "
+              "w1w3 body %.2f | -> w2 input %.2f | w2 body %.2f | -> next qkv input %.2f | layer %.2f"
+              % tuple(m))
+        # which attention CTAs finish last, and how their time splits (thread 0 cycles)
+        b = (L // 2) * NPL
+        order = np.argsort(-st[:n_attn, b + k_attn, 2])[:6]
+        q_done = st[:, b + k_qkv, 2].max()
+        for c in order:
+            cy = cyc[c, b + k_attn] / ghz / 1e3
+            print(f"#   layer {L // 2}: attention CTA {c} (head {c // sp}, split {c % sp}) entered {st[c, b + k_attn, 0] - q_done:+.2f}, "
+                  f"done {st[c, b + k_attn, 2] - q_done:+.2f} vs last qkv row; polls+rope {cy[0]:.2f} scores {cy[1]:.2f} merges {cy[2]:.2f} "
+                  f"pv {cy[3]:.2f} ringwait {cy[4]:.2f}")
+        # who finishes the qkv phase last (the rows every attention CTA waits for)
+        order = np.argsort(-st[:, b + k_qkv, 2])[:4]
+        print("#   layer %d: last qkv CTAs %s finish %s us after the median CTA" % (
+            L // 2, list(order), np.round(st[order, b + k_qkv, 2] - np.median(st[:, b + k_qkv, 2]), 2)))
 
 
 if __name__ == "__main__":
