@@ -602,7 +602,7 @@ def run_ours(args, rank, world):
                        "l2": "no flush: every step streams %.2f GB of weights per GPU >> 126 MB L2" % (res["bytes_gpu"] / 1e9),
                        "weight_bytes_per_token": res["bytes_tok"], "launches_per_step": b.launches_per_step,
                        "engine": b.engine,
-                       "numerics": "fast: free summation order (int8 rows on dp4a with 24-bit fixed-point activations, "
+                       "numerics": "fast: free summation order (int8 rows as int8 weights x 24-bit fixed-point activations on mma.sync s8 / dp4a, "
                                    "flash-decoding attention), logits within 1e-4 of the exact mode "
                                    "(tests/test_decoder_gpu.py::test_fast_numerics_within_north_star_tolerance); "
                                    "exact-mode numbers under \"exact\"" if b.numerics == "fast" else

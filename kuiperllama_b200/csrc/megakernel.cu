@@ -248,6 +248,7 @@ __shared__ float g_s_argv[kMaxWarps];
 __shared__ int g_s_argi[kMaxWarps];
 __shared__ float g_s_bcast;
 __shared__ volatile unsigned g_fill_count;  // ring stages the producer has issued so far
+__shared__ float g_s_pair[kMaxWarps / 2][2][8];  // mma form: the odd warp's row partials, double buffered per pair
 __shared__ Phase g_ph_cons;
 __shared__ Phase g_ph_prod;
 __shared__ Phase g_ph_pf;
@@ -534,6 +535,59 @@ __device__ __forceinline__ void accum_w8_dp4a(const uint32_t (&w)[NR], const uin
       }
     }
   }
+}
+
+// ---- int8 weights x fixed-point activations on the tensor cores (TOLERANCED, same numbers as above) ----------
+// The integer dot-product unit runs at a quarter of the FP32 rate on sm_100 (measured: the dp4a rows above are
+// bound by it, 12 IDP.4A per 16 weights), so where a ring stage holds several rows that share the input
+// vector -- every matrix with 4096-byte rows -- the 64-element groups go through mma.sync m16n8k32 (s8 x s8 ->
+// s32, SASS IMMA.16832.S8.S8) instead:
+//     A (16 x 32, row major)  rows 0..7 = the (up to 8) weight rows of the stage, rows 8..15 mirror them
+//     B (32 x 8, column major) columns 0, 1, 2 = the three digit planes of x, columns 3..7 = 0
+//     D (16 x 8, s32)          D[r][k] = sum_i w[r][i] * l_k[i]  -- the exact integers D_k of the dp4a form
+// two mma per group (K = 2 x 32); the lane that holds D[r][0..1] fetches D[r][2] from its neighbour and adds
+// s_g * step_g * (65536 D2 + 256 D1 + D0) to the row's running sum.  A PAIR of warps takes a whole stage (the
+// ring holds only six stages: one warp per stage would leave most consumer warps idle): the even warp the first
+// half of the groups, the odd warp the second half; the halves meet through shared memory.  Rows are
+// staged `row_stride` bytes apart = row length + 16, which spreads the eight rows of a fragment load over all
+// 32 banks (row r, k-quad t -> bank 4 r + t); the scale rows likewise.
+// Result: lane 4 r holds the total of row r (rows >= nrows repeat row nrows - 1).
+__device__ __forceinline__ void mma_s8(int (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+      : "r"(a0), "r"(a0), "r"(a2), "r"(a2), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float accum_w8_mma(uint32_t w_base, uint32_t row_stride, uint32_t sc_base, uint32_t sc_stride,
+                                              int nrows, uint32_t x, int g_begin, int g_end, int lane) {
+  const int gid = lane >> 2, tig = lane & 3;
+  const int r = min(gid, nrows - 1);
+  const uint32_t wrow = w_base + static_cast<uint32_t>(r) * row_stride + static_cast<uint32_t>(tig) * 4u;
+  const uint32_t srow = sc_base + static_cast<uint32_t>(r) * sc_stride;
+  const uint32_t plane = static_cast<uint32_t>(min(gid, 2));
+  const bool bcol = gid < 3;
+  float acc = 0.f;
+#pragma unroll 2
+  for (int g = g_begin; g < g_end; ++g) {
+    const uint32_t odd = static_cast<uint32_t>(g) & 1u;
+    const uint32_t xg = x + static_cast<uint32_t>(g) * 256u;
+    const uint32_t pb = xg + ((plane + odd) & 3u) * 64u + static_cast<uint32_t>(tig) * 4u;
+    uint32_t b0 = lds_u32(pb), b1 = lds_u32(pb + 16), b2 = lds_u32(pb + 32), b3 = lds_u32(pb + 48);
+    if (!bcol) b0 = b1 = b2 = b3 = 0u;
+    const uint32_t wa = wrow + static_cast<uint32_t>(g) * 64u;
+    const uint32_t a0 = lds_u32(wa), a1 = lds_u32(wa + 16), a2 = lds_u32(wa + 32), a3 = lds_u32(wa + 48);
+    const float xstep = lds_f32(xg + ((3u + odd) & 3u) * 64u);
+    const float ws = lds_f32(srow + static_cast<uint32_t>(g) * 4u);
+    int c[4] = {0, 0, 0, 0};
+    mma_s8(c, a0, a1, b0, b1);  // elements 0..31 of the group
+    mma_s8(c, a2, a3, b2, b3);  // elements 32..63
+    // c[0] = D[row gid][column 2 tig], c[1] = D[row gid][column 2 tig + 1]: |D| <= 64 * 128 * 128 = 2^20
+    const int d2 = __shfl_down_sync(kFull, c[0], 1);  // for the tig == 0 lanes: column 2 lives in tig 1
+    const float f = __fmaf_rn(small_int_to_float(d2), 65536.0f,
+                              __fmaf_rn(small_int_to_float(c[1]), 256.0f, small_int_to_float(c[0])));
+    acc = __fmaf_rn(f, __fmul_rn(xstep, ws), acc);
+  }
+  return acc;
 }
 
 // The phase's input vector (fp32, M floats at xs, M % 64 == 0) -> digit planes + step per group, in
@@ -1786,6 +1840,39 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
       const long long c1 = stamp ? clock64() : 0;
       cyc_wait += c1 - c0;
       const unsigned char* sbase = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
+      if constexpr (INT8) {
+        if (ph.mma && int8_fast) {  // the whole stage (<= 8 rows) is one warp PAIR's task on the tensor cores
+          constexpr int kPairs = CW / 2;
+          const int pair = warp >> 1, half = warp & 1;
+          if (task % kPairs == pair) {
+            const int j = lane >> 2;  // lane 4 j ends with the total of stage row j
+            const bool owner = half == 0 && (lane & 3) == 0 && j < n;
+            float bias_v = 0.f, res_v = 0.f;
+            if (owner) prefetch_addend(u + j, bias_v, res_v);
+            const uint32_t pad = static_cast<uint32_t>(ph.row_pad);
+            const int groups = M >> 6, g_mid = (groups + 1) >> 1;
+            float tot = accum_w8_mma(smem_u32(sbase), static_cast<uint32_t>(row_bytes) + pad,
+                                     smem_u32(sbase) + static_cast<uint32_t>(ph.scale_off),
+                                     static_cast<uint32_t>(ph.scale_row_bytes) + pad, n * rpu, smem_u32(xs),
+                                     half ? g_mid : 0, half ? groups : g_mid, lane);
+            float* scratch = g_s_pair[pair][(task / kPairs) & 1];
+            if (half == 1 && (lane & 3) == 0) scratch[j] = tot;
+            asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory");  // the two warps of the pair
+            if (half == 0) {
+              tot = __fadd_rn(tot, scratch[j]);
+              // SwiGLU stage order: w1 rows of the n units, then their w3 rows
+              const float tot_w3 = __shfl_sync(kFull, tot, min(j + n, 7) * 4);
+              if (owner) epilogue(u + j, tot, tot_w3, bias_v, res_v);
+            }
+          }
+          ++task;
+          __syncwarp();
+          if (stamp) cyc_rows += clock64() - c1;
+          if (lane == 0) mbar_arrive(&empty_bar[pipe.slot]);
+          pipe.advance(S);
+          continue;
+        }
+      }
       for (int i0 = 0; i0 < n; i0 += upt, ++task) {
         if (task % CW != warp) continue;  // CW is 6, 8 or 16: a real modulo (a mask would idle warps 2 and 3 of 6)
         const int nu = min(upt, n - i0);
@@ -1877,7 +1964,7 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
     // that ran epilogues hold partial bests
     ArgBest wb = best;
 #pragma unroll
-    for (int off = 1; off < 4; off <<= 1) {
+    for (int off = 1; off < 32; off <<= 1) {  // (the mma form runs its epilogues in lanes 0, 4, ..., 28)
       const float ov = __shfl_xor_sync(kFull, wb.v, off);
       const int oi = __shfl_xor_sync(kFull, wb.i, off);
       arg_fold(wb, ov, oi);
@@ -2105,7 +2192,24 @@ __global__ void __launch_bounds__(CW * 32 + 64, 1) decode_megakernel(const __gri
               mbar_expect_tx(&full_bar[pipe.slot],
                              static_cast<uint32_t>(nrows) * (row_bytes + ph.scale_row_bytes));
             __syncwarp();
-            {  // one bulk copy per run of consecutive rows of one matrix (nrows <= 32: lane = row)
+            if (ph.row_pad) {
+              // padded rows (mma form, nrows <= 8): one copy per weight row (lanes 0..7) and per scale row (16..23)
+              const int j = lane & 15;
+              if (j < nrows && (lane & 8) == 0) {
+                const RowRef rr = stage_row(ph, u, n, j);
+                const long long e = static_cast<long long>(rr.row) * ph.in_dim;
+                if (lane < 16) {
+                  bulk_g2s(dst + static_cast<size_t>(j) * (row_bytes + ph.row_pad),
+                           static_cast<const unsigned char*>(ph.seg[rr.seg].w) + e * wbytes, static_cast<uint32_t>(row_bytes),
+                           &full_bar[pipe.slot], policy);
+                } else {
+                  const long long g0 = ph.group_shift >= 0 ? (e >> ph.group_shift) : (e / ph.group_size);
+                  bulk_g2s(dst + ph.scale_off + static_cast<size_t>(j) * (ph.scale_row_bytes + ph.row_pad),
+                           ph.seg[rr.seg].scales + g0, static_cast<uint32_t>(ph.scale_row_bytes), &full_bar[pipe.slot],
+                           policy);
+                }
+              }
+            } else {  // one bulk copy per run of consecutive rows of one matrix (nrows <= 32: lane = row)
               const RowRef rr = lane < nrows ? stage_row(ph, u, n, lane) : RowRef{-1, -1};
               const int len = run_length(rr, lane, nrows);
               if (len > 0) {
@@ -2451,7 +2555,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   }
   xbuf = (xbuf + 127) & ~127;
   const int xres = tagged_ ? ((dim * 4 + 127) & ~127) : 0;  // the CTA's copy of the residual stream
-  const int budget = max_smem - xbuf - xres - 2048;  // static shared memory + slack
+  const int budget = max_smem - xbuf - xres - 3072;  // static shared memory (2 KB) + slack
   int stages = budget / stage_bytes;
   if (stages > mega::kMaxStages) stages = mega::kMaxStages;
   if (const char* e = getenv("KLLM_STAGES")) stages = std::min(stages, atoi(e));
@@ -2489,16 +2593,20 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
 
   // ---- phase table ---------------------------------------------------------------------------------
   std::vector<Phase> ph;
-  // Rows per consumer task (1, 2 or 4) of a phase.  A CTA owns only 14-84 rows of a phase; its tasks go
-  // round-robin over the consumer warps, so the phase takes `rounds` x (time of one task), and a task of
-  // NR rows costs about NR + x_cost (the NR rows share each load of the input vector; fp32 rows are
-  // bound by shared-memory loads: x_cost 1, int8 rows by their arithmetic: x_cost 0.5).  Pick the
-  // cheapest; ties go to the fatter task.  KLLM_TASK_ROWS_RT=1|2|4 forces one size for every phase.
-  int forced_task_rows = 0;
+  // Rows per consumer task (1, 2 or 4) of a phase.  Measured on B200 (profiles/README.md, passes Q and R):
+  // 4 everywhere is best or equal (TinyLlama 1105 vs 1082 "auto" vs 1068 with 2; Llama-2-7B int8 418 / 405 /
+  // 407) -- the four rows of a task share every load of the input vector, and that outweighs the better
+  // balance of small tasks.  KLLM_TASK_ROWS_RT=1|2|4 forces a size, =auto picks per phase with the cost model
+  // below (rounds x (rows + x_cost), tasks never crossing a ring stage).
+  int forced_task_rows = 4;
   if (const char* e = getenv("KLLM_TASK_ROWS_RT")) {
     const int v = atoi(e);
     if (v == 1 || v == 2 || v == 4) forced_task_rows = v;
+    if (std::string(e) == "auto") forced_task_rows = 0;
   }
+  // KLLM_INT8_MMA=0: keep every int8 row on the dp4a form
+  bool int8_mma = true;
+  if (const char* e = getenv("KLLM_INT8_MMA")) int8_mma = atoi(e) != 0;
   auto pick_task_rows = [&](Phase& p) {
     const int rpu = p.swiglu ? 2 : 1;
     p.task_rows = 4;
@@ -2533,6 +2641,24 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
     }
     p.scale_row_bytes = int8 ? (p.in_dim / m.group_size) * 4 : 0;
     const int rpu = p.swiglu ? 2 : 1;
+    // int8 fast mode: stages that hold >= 3 rows go through the tensor cores (accum_w8_mma): <= 8 rows per
+    // stage, rows and scale rows staged 16 bytes apart more than their length
+    p.mma = 0, p.row_pad = 0;
+    if (int8_fast_ && int8_mma && m.group_size == 64 && p.in_dim % 64 == 0) {
+      const int padded = row_bytes + 16 + p.scale_row_bytes + 16;
+      int rows = std::min(8, stage_bytes / padded);
+      rows -= rows % rpu;
+      while (rows >= 3 && ((rows * (row_bytes + 16) + 127) & ~127) + rows * (p.scale_row_bytes + 16) > stage_bytes) rows -= rpu;
+      if (rows >= 3) {
+        p.mma = 1, p.row_pad = 16;
+        p.rows_per_stage = rows;
+        p.chunks_per_row = 1;
+        p.chunk_elems = p.in_dim;
+        p.scale_off = (rows * (row_bytes + 16) + 127) & ~127;
+        pick_task_rows(p);
+        return 0;
+      }
+    }
     const int per_row = row_bytes + p.scale_row_bytes;
     if (per_row * rpu <= stage_bytes) {
       int rows = stage_bytes / per_row;
