@@ -248,7 +248,7 @@ __shared__ float g_s_argv[kMaxWarps];
 __shared__ int g_s_argi[kMaxWarps];
 __shared__ float g_s_bcast;
 __shared__ volatile unsigned g_fill_count;  // ring stages the producer has issued so far
-__shared__ float g_s_pair[kMaxWarps / 2][2][8];  // mma form: the odd warp's row partials, double buffered per pair
+__shared__ float g_s_team[kMaxWarps / 2][2][3][8];  // team form: the other members' row partials, double buffered per team
 __shared__ Phase g_ph_cons;
 __shared__ Phase g_ph_prod;
 __shared__ Phase g_ph_pf;
@@ -505,7 +505,7 @@ __device__ __forceinline__ float small_int_to_float(int d) {
 // plane is the 16-byte chunk q of its region.
 template <int NR>
 __device__ __forceinline__ void accum_w8_dp4a(const uint32_t (&w)[NR], const uint32_t (&sc)[NR], uint32_t x, int M,
-                                              int lane, float (&acc)[NR]) {
+                                              int lane, float (&acc)[NR], int it_begin = 0, int it_end = 1 << 30) {
   // lane owns 16 consecutive elements per step of 512: group = 8 * step + lane / 4, quarter = lane % 4
   const uint32_t odd = (lane >> 2) & 1u;
   const uint32_t gq = x + (lane >> 2) * 256 + (lane & 3) * 16;
@@ -517,9 +517,9 @@ __device__ __forceinline__ void accum_w8_dp4a(const uint32_t (&w)[NR], const uin
     wp[r] = w[r] + lane * 16;
     sp[r] = sc[r] + (lane >> 2) * 4;
   }
-  const int steps = (M + 511) >> 9;
+  const int steps = min((M + 511) >> 9, it_end);
 #pragma unroll 2
-  for (int it = 0; it < steps; ++it) {
+  for (int it = it_begin; it < steps; ++it) {
     if (it * 512 + lane * 16 < M) {  // M % 512 != 0: the last step covers part of the lanes (M % 64 == 0)
       const uint4 a0 = lds_u4(l0 + it * 2048), a1 = lds_u4(l1 + it * 2048), a2 = lds_u4(l2 + it * 2048);
       const float xstep = lds_f32(xsp + it * 2048);
@@ -1841,25 +1841,49 @@ __device__ KLLM_PHASE_CALL Carry gemv_phase(const Params& P, Carry carry, int to
       cyc_wait += c1 - c0;
       const unsigned char* sbase = stages + static_cast<size_t>(pipe.slot) * P.stage_bytes;
       if constexpr (INT8) {
-        if (ph.mma && int8_fast) {  // the whole stage (<= 8 rows) is one warp PAIR's task on the tensor cores
-          constexpr int kPairs = CW / 2;
-          const int pair = warp >> 1, half = warp & 1;
-          if (task % kPairs == pair) {
+        if (ph.team && int8_fast) {
+          // TEAM form.  With one task per warp the (six) stages of the ring are consumed side by side and
+          // released together: the producer cannot refill while the consumers compute, and a phase takes the
+          // sum of both (measured: int8 rows at half the HBM rate).  Here kTeam warps share ONE stage -- each
+          // takes a slice of the columns of all its rows -- so stages are finished and released one after the
+          // other and the refill of the first overlaps the arithmetic on the next.  Member 0 adds the members'
+          // row partials (in member order, through shared memory) and runs the epilogues.
+          constexpr int kTeam = (CW % 4 == 0) ? 4 : 2, kTeams = CW / kTeam;
+          const int team = warp / kTeam, member = warp % kTeam;
+          if (task % kTeams == team) {
             const int j = lane >> 2;  // lane 4 j ends with the total of stage row j
-            const bool owner = half == 0 && (lane & 3) == 0 && j < n;
+            const bool owner = member == 0 && (lane & 3) == 0 && j < n;
             float bias_v = 0.f, res_v = 0.f;
             if (owner) prefetch_addend(u + j, bias_v, res_v);
-            const uint32_t pad = static_cast<uint32_t>(ph.row_pad);
-            const int groups = M >> 6, g_mid = (groups + 1) >> 1;
-            float tot = accum_w8_mma(smem_u32(sbase), static_cast<uint32_t>(row_bytes) + pad,
-                                     smem_u32(sbase) + static_cast<uint32_t>(ph.scale_off),
-                                     static_cast<uint32_t>(ph.scale_row_bytes) + pad, n * rpu, smem_u32(xs),
-                                     half ? g_mid : 0, half ? groups : g_mid, lane);
-            float* scratch = g_s_pair[pair][(task / kPairs) & 1];
-            if (half == 1 && (lane & 3) == 0) scratch[j] = tot;
-            asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory");  // the two warps of the pair
-            if (half == 0) {
-              tot = __fadd_rn(tot, scratch[j]);
+            const int nrows = n * rpu;
+            float tot = 0.f;
+            if (ph.mma) {  // <= 8 rows on the tensor cores; the member's share of the 64-element groups
+              const uint32_t pad = static_cast<uint32_t>(ph.row_pad);
+              const int groups = M >> 6;
+              tot = accum_w8_mma(smem_u32(sbase), static_cast<uint32_t>(row_bytes) + pad,
+                                 smem_u32(sbase) + static_cast<uint32_t>(ph.scale_off),
+                                 static_cast<uint32_t>(ph.scale_row_bytes) + pad, nrows, smem_u32(xs),
+                                 groups * member / kTeam, groups * (member + 1) / kTeam, lane);
+            } else {  // one or two long rows on dp4a; the member's share of the 512-element steps
+              const int steps = (M + 511) >> 9;
+              const uint32_t wa = smem_u32(sbase), sa = wa + static_cast<uint32_t>(ph.scale_off);
+              const uint32_t w2[2] = {wa, wa + (nrows > 1 ? static_cast<uint32_t>(row_bytes) : 0u)};
+              const uint32_t s2[2] = {sa, sa + (nrows > 1 ? static_cast<uint32_t>(ph.scale_row_bytes) : 0u)};
+              float a2[2] = {0.f, 0.f};
+              accum_w8_dp4a<2>(w2, s2, smem_u32(xs), M, lane, a2, steps * member / kTeam, steps * (member + 1) / kTeam);
+#pragma unroll
+              for (int off = 16; off > 0; off >>= 1) {
+                a2[0] += __shfl_xor_sync(kFull, a2[0], off);
+                a2[1] += __shfl_xor_sync(kFull, a2[1], off);
+              }
+              tot = j == 0 ? a2[0] : a2[1];
+            }
+            float* scratch = &g_s_team[team][(task / kTeams) & 1][0][0];
+            if (member != 0 && (lane & 3) == 0) scratch[(member - 1) * 8 + j] = tot;
+            asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "n"(kTeam * 32) : "memory");  // the warps of the team
+            if (member == 0) {
+#pragma unroll
+              for (int mm = 1; mm < kTeam; ++mm) tot = __fadd_rn(tot, scratch[(mm - 1) * 8 + j]);
               // SwiGLU stage order: w1 rows of the n units, then their w3 rows
               const float tot_w3 = __shfl_sync(kFull, tot, min(j + n, 7) * 4);
               if (owner) epilogue(u + j, tot, tot_w3, bias_v, res_v);
@@ -2460,6 +2484,7 @@ const void* kernel_for(int consumer_warps, bool int8) {
   if (int8) {
     if (consumer_warps == 16) return reinterpret_cast<const void*>(mega::decode_megakernel<16, true, PROF>);
     if (consumer_warps == 14) return reinterpret_cast<const void*>(mega::decode_megakernel<14, true, PROF>);
+    if (consumer_warps == 12) return reinterpret_cast<const void*>(mega::decode_megakernel<12, true, PROF>);
     if (consumer_warps == 6) return reinterpret_cast<const void*>(mega::decode_megakernel<6, true, PROF>);
     return reinterpret_cast<const void*>(mega::decode_megakernel<8, true, PROF>);
   }
@@ -2498,15 +2523,15 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
     for (int d : dims)
       if (d % m.group_size != 0 || ((d / m.group_size) * 4) % 16 != 0) return KLLM_E_UNSUPPORTED;
   }
-  // consumer warps (+ the ring producer and the L2 prefetcher): fp32 rows 8 x 168 registers; int8 rows are
-  // bound by instruction issue and want many warps -- 14, so that the CTA is 16 warps = 4 per scheduler with
-  // 128 registers each (16 consumers make 18 warps, which caps them at 96 registers and spills).  Measured on
-  // B200 (profiles/README.md, pass Q): fp32 6 vs 8 warps 1072 = 1072 (TinyLlama), 1218 < 1296 (Qwen2.5-0.5B),
-  // 210 < 213 (Llama-2-7B); int8 16 / 14 / 8 warps 394 / 400 / 375 tok/s.
-  consumer_warps_ = int8 ? 14 : 8;
+  // consumer warps (+ the ring producer and the L2 prefetcher): fp32 rows 8 x 168 registers; int8 rows 12 =
+  // three teams of four that share a ring stage each (gemv_phase, team form), so that the CTA is 14 warps with
+  // 128 registers (16 consumers make 18 warps, which caps them at 96 registers and spills).  Measured on B200
+  // (profiles/README.md): fp32 6 vs 8 warps 1072 = 1072 (TinyLlama), 1218 < 1296 (Qwen2.5-0.5B), 210 < 213
+  // (Llama-2-7B); int8 before the team form 16 / 14 / 8 warps 394 / 400 / 375 tok/s.
+  consumer_warps_ = int8 ? 12 : 8;
   if (const char* e = getenv("KLLM_CONSUMER_WARPS")) {
     const int v = atoi(e);
-    if (int8 && (v == 6 || v == 8 || v == 14 || v == 16)) consumer_warps_ = v;  // fast mode: CT >= 192 quantises M <= 16384 in <= 6 rounds
+    if (int8 && (v == 6 || v == 8 || v == 12 || v == 14 || v == 16)) consumer_warps_ = v;  // fast mode: CT >= 192 quantises M <= 16384 in <= 6 rounds
     if (!int8 && (v == 6 || v == 8)) consumer_warps_ = v;
   }
   // int8 arithmetic: "exact" reproduces the reference's fma(x * scale, float(w), acc) per element bit for
@@ -2555,7 +2580,7 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
   }
   xbuf = (xbuf + 127) & ~127;
   const int xres = tagged_ ? ((dim * 4 + 127) & ~127) : 0;  // the CTA's copy of the residual stream
-  const int budget = max_smem - xbuf - xres - 3072;  // static shared memory (2 KB) + slack
+  const int budget = max_smem - xbuf - xres - 3584;  // static shared memory (3 KB) + slack
   int stages = budget / stage_bytes;
   if (stages > mega::kMaxStages) stages = mega::kMaxStages;
   if (const char* e = getenv("KLLM_STAGES")) stages = std::min(stages, atoi(e));
@@ -2643,14 +2668,14 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
     const int rpu = p.swiglu ? 2 : 1;
     // int8 fast mode: stages that hold >= 3 rows go through the tensor cores (accum_w8_mma): <= 8 rows per
     // stage, rows and scale rows staged 16 bytes apart more than their length
-    p.mma = 0, p.row_pad = 0;
+    p.mma = 0, p.row_pad = 0, p.team = 0;
     if (int8_fast_ && int8_mma && m.group_size == 64 && p.in_dim % 64 == 0) {
       const int padded = row_bytes + 16 + p.scale_row_bytes + 16;
       int rows = std::min(8, stage_bytes / padded);
       rows -= rows % rpu;
       while (rows >= 3 && ((rows * (row_bytes + 16) + 127) & ~127) + rows * (p.scale_row_bytes + 16) > stage_bytes) rows -= rpu;
       if (rows >= 3) {
-        p.mma = 1, p.row_pad = 16;
+        p.mma = 1, p.row_pad = 16, p.team = 1;
         p.rows_per_stage = rows;
         p.chunks_per_row = 1;
         p.chunk_elems = p.in_dim;
@@ -2664,6 +2689,8 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
       int rows = stage_bytes / per_row;
       rows -= rows % rpu;
       rows = std::min(rows, 32);  // one bulk copy per producer lane
+      // int8 fast mode, one or two long rows per stage (hidden_dim columns): a team of warps on dp4a
+      if (int8_fast_ && int8_mma && m.group_size == 64 && p.in_dim % 64 == 0 && rows <= 2) p.team = 1;
       p.rows_per_stage = rows;
       p.chunks_per_row = 1;
       p.chunk_elems = p.in_dim;

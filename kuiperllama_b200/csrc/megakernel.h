@@ -46,7 +46,8 @@ struct Phase {
   int group_size, group_shift;
   int rows_per_stage;     // whole rows per ring stage (chunks_per_row == 1)
   int task_rows;          // rows handed to one consumer warp at a time (1, 2 or 4; picked per phase at init)
-  int mma;                // int8 fast mode: the rows of a stage go through mma.sync m16n8k32 s8 (one warp per stage)
+  int mma;                // int8 fast mode: the rows of a stage go through mma.sync m16n8k32 s8
+  int team;               // int8 fast mode: a TEAM of consumer warps shares each ring stage, splitting the columns
   int row_pad;            // ... and are staged row_pad bytes apart more than their length (bank-conflict-free fragments)
   int chunks_per_row;     // > 1: a row spans this many stages (fp32 rows longer than a stage)
   int chunk_elems;
