@@ -2523,12 +2523,12 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
     for (int d : dims)
       if (d % m.group_size != 0 || ((d / m.group_size) * 4) % 16 != 0) return KLLM_E_UNSUPPORTED;
   }
-  // consumer warps (+ the ring producer and the L2 prefetcher): fp32 rows 8 x 168 registers; int8 rows 12 =
-  // three teams of four that share a ring stage each (gemv_phase, team form), so that the CTA is 14 warps with
-  // 128 registers (16 consumers make 18 warps, which caps them at 96 registers and spills).  Measured on B200
-  // (profiles/README.md): fp32 6 vs 8 warps 1072 = 1072 (TinyLlama), 1218 < 1296 (Qwen2.5-0.5B), 210 < 213
-  // (Llama-2-7B); int8 before the team form 16 / 14 / 8 warps 394 / 400 / 375 tok/s.
-  consumer_warps_ = int8 ? 12 : 8;
+  // consumer warps (+ the ring producer and the L2 prefetcher): fp32 rows 8 x 168 registers; int8 rows 14, so
+  // that the CTA is 16 warps = 4 per scheduler with 128 registers each (16 consumers make 18 warps, which caps
+  // them at 96 registers and spills).  Measured on B200 (profiles/README.md, passes Q-T): fp32 6 vs 8 warps
+  // 1072 = 1072 (TinyLlama), 1218 < 1296 (Qwen2.5-0.5B), 210 < 213 (Llama-2-7B); int8 16 / 14 / 8 warps
+  // 394 / 400 / 375 tok/s.
+  consumer_warps_ = int8 ? 14 : 8;
   if (const char* e = getenv("KLLM_CONSUMER_WARPS")) {
     const int v = atoi(e);
     if (int8 && (v == 6 || v == 8 || v == 12 || v == 14 || v == 16)) consumer_warps_ = v;  // fast mode: CT >= 192 quantises M <= 16384 in <= 6 rounds
@@ -2629,8 +2629,12 @@ int MegaEngine::init(const MegaModel& m, cudaStream_t stream) {
     if (v == 1 || v == 2 || v == 4) forced_task_rows = v;
     if (std::string(e) == "auto") forced_task_rows = 0;
   }
-  // KLLM_INT8_MMA=0: keep every int8 row on the dp4a form
-  bool int8_mma = true;
+  // KLLM_INT8_MMA=1: int8 fast rows in the team form -- mma.sync m16n8k32 s8 for stages of 3-8 rows, dp4a with the
+  // columns split over the team for 1-2 long rows.  Correct (the parity suite passes with it) but not faster on
+  // B200: Llama-2-7B int8 398 (teams of 4, 12 warps) / 403 (pairs, 14 warps) vs 407 tok/s for the plain dp4a
+  // rows (profiles/README.md, passes S and T) -- at one byte per weight the shared-memory reads of the
+  // fragments cost what the dp4a arithmetic costs.  Off by default.
+  bool int8_mma = false;
   if (const char* e = getenv("KLLM_INT8_MMA")) int8_mma = atoi(e) != 0;
   auto pick_task_rows = [&](Phase& p) {
     const int rpu = p.swiglu ? 2 : 1;
