@@ -13,7 +13,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 LIB = ROOT / "kuiperllama_b200" / "lib" / "libkllm_b200.so"
-KEY = ["UBLKCP", "UBLKPF", "UTMALDG", "UTMASTG", "UTCHMMA", "UTCQMMA", "UTCIMMA", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS",
+KEY = ["UBLKCP", "UBLKPF", "UTMALDG", "UTMASTG", "UTCHMMA", "UTCQMMA", "UTCIMMA", "LDTM", "STTM", "UTCBAR", "UTCATOMSWS", "IMMA",
        "SYNCS", "IDP", "FFMA", "FADD", "FMUL", "PRMT", "I2F", "LDS", "STS", "LDG", "STG", "LD", "ST", "SHFL", "MUFU",
        "BAR", "HMMA", "NANOSLEEP", "CCTL", "ATOM", "RED", "MEMBAR", "LDL", "STL"]
 
