@@ -16,12 +16,16 @@
 // classifier + greedy argmax.  RoPE moves into the attention phase so GEMV rows can be split
 // evenly over all SMs.
 //
-// Consumers (CW warps: 8 for fp32 weights, 16 for int8): the rows of a ring stage are handed out
-// as TASKS of up to four rows to one warp each, round-robin.  A task's rows share every load of
-// the input vector (shared-memory bandwidth is what bounds an fp32 row; instruction issue an
-// int8 row), their dot-product chains interleave (ILP instead of occupancy), their totals are
-// folded with "packed" shuffle trees (kllm_device.cuh) that do the additions of cub's tree only,
-// and one lane per row runs the epilogues side by side.
+// Consumers (CW warps: 8 for fp32 weights, 14 for int8): the rows of a ring stage are handed out as TASKS of
+// up to four rows to one warp each, round-robin.  A task's rows share every load of the input vector, their
+// dot-product chains interleave (ILP instead of occupancy), their totals are folded with "packed" shuffle trees
+// (kllm_device.cuh) that do the additions of cub's tree only, and one lane per row runs the epilogues side by
+// side.  (int8, toleranced mode, opt-in: a team of warps shares a stage -- mma.sync s8 or dp4a; gemv_phase.)
+//
+// No local memory: the ring takes the whole unified L1, so a stack access is a round trip to L2.  The kernel
+// parameters are __grid_constant__ (never copied to the stack), register buffers are always written in full
+// (a conditionally written element forces the array into local memory), nothing indexes an array at run time.
+// `cuobjdump -res-usage` / tools/sass_histogram.py (profiles/r02_sass_histogram.txt) show what is left.
 //
 // Hand-over between phases (KLLM_MEGA_TAGGED=2, default): every produced element is published as
 // one 64-bit {tag, fp32} word and polled in place by the consuming phase -- no fences, flags or

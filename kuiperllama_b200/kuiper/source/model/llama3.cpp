@@ -16,9 +16,7 @@
 
 #include <cuda_runtime_api.h>
 #include <kllm_b200.h>
-#include <op/matmul.h>
-#include <op/mha.h>
-#include <op/rmsnorm.h>
+#include <op/decoder_layers.h>
 
 #include <cstring>
 #include <utility>

@@ -1,13 +1,7 @@
 // The compute layers: thin shape/device validation + registry dispatch
 // (reference kuiper/source/op/{add,swiglu,rmsnorm,rope,mha,matmul,embedding}.cpp).
 #include "kernels/kernels_interface.h"
-#include "op/add.h"
-#include "op/embedding.h"
-#include "op/matmul.h"
-#include "op/mha.h"
-#include "op/rmsnorm.h"
-#include "op/rope.h"
-#include "op/swiglu.h"
+#include "op/decoder_layers.h"
 
 namespace op {
 namespace {

@@ -21,7 +21,7 @@
 #include "model/llama3.h"
 #include "model/qwen2.h"
 #include "model/tensor_parallel.h"
-#include "op/matmul.h"
+#include "op/decoder_layers.h"
 
 namespace model {
 struct ModelInspector {
