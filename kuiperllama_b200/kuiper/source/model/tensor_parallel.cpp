@@ -143,6 +143,8 @@ base::Status TpRendezvous::open(const TpConfig& cfg, int timeout_s) {
       const int fd = ::accept(listen_fd_, nullptr, nullptr);
       if (fd < 0) return InternalError("tensor parallel rendezvous: a rank did not show up");
       ::setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+      const timeval patience{10 * timeout_s, 0};  // a peer that stops answering ends in an error, not a hang
+      ::setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &patience, sizeof(patience));
       int32_t who = -1;
       if (!recv_all(fd, &who, sizeof(who)) || who <= 0 || who >= world_ || peers_[who] >= 0) {
         ::close(fd);
@@ -163,6 +165,8 @@ base::Status TpRendezvous::open(const TpConfig& cfg, int timeout_s) {
       std::this_thread::sleep_for(std::chrono::milliseconds(50));
     }
     ::setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+    const timeval patience{10 * timeout_s, 0};
+    ::setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &patience, sizeof(patience));
     const int32_t who = rank_;
     if (!send_all(fd, &who, sizeof(who))) {
       ::close(fd);
