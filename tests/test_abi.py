@@ -60,3 +60,30 @@ def test_argument_validation_without_device(kllm_lib):
     assert kllm_lib.kllm_gemv_f32(None, None, None, 4, 4, None) == -1
     assert kllm_lib.kllm_rmsnorm_f32(None, None, None, 0, 1e-5, None) == -1
     assert kllm_lib.kllm_decoder_create(None, None, None) == -1
+
+
+def test_megakernel_keeps_its_state_out_of_local_memory(kllm_lib):
+    """The persistent kernel's ring takes the whole unified L1, so a local-memory access is a round trip to L2
+    ("No local memory").  Gate: the default instantiations -- 8 fp32 and 14 int8 consumer warps --
+    carry no parameter copy on the stack (it was 456 bytes before the parameters became __grid_constant__) and
+    only a handful of local loads / stores (per-token spills and the cold trap-message path), none of them in
+    the row loops' register budget class; nvcc / ptxas regressions of that kind show up here, on the CPU."""
+    import re
+    import subprocess
+    from kuiperllama_b200 import build as kbuild
+    lib = str(kbuild.LIB)
+    res = subprocess.run(["cuobjdump", "-res-usage", lib], capture_output=True, text=True, check=True).stdout
+    usage = {}
+    for m in re.finditer(r"Function (\S+):\s*\n\s*REG:(\d+) STACK:(\d+)", res):
+        usage[m.group(1)] = (int(m.group(2)), int(m.group(3)))
+    defaults = {"_ZN4kllm4mega17decode_megakernelILi8ELb0ELb0EEEvNS0_6ParamsE": 168,
+                "_ZN4kllm4mega17decode_megakernelILi14ELb1ELb0EEEvNS0_6ParamsE": 128}
+    for name, reg_cap in defaults.items():
+        assert name in usage, sorted(k for k in usage if "megakernel" in k)
+        regs, stack = usage[name]
+        assert regs <= reg_cap, (name, regs)
+        assert stack <= 64, f"{name}: {stack} bytes of stack (a parameter copy or a local array is back)"
+        sass = subprocess.run(["cuobjdump", "-sass", "-fun", name, lib], capture_output=True, text=True, check=True).stdout
+        local = len(re.findall(r"\b(?:LDL|STL)\b", sass))
+        assert local <= 32, f"{name}: {local} local-memory instructions"
+        assert "UBLKCP" in sass and "SYNCS" in sass  # TMA bulk copies + mbarriers are what feeds the ring
