@@ -103,11 +103,14 @@ LOAD_CASES = {
     "fp32-kv-replicated": (ModelShape("tp-kvrep", 128, 256, 2, 4, 1, 96, 32), "llama", "fp32", "llama2"),
     "int8": (ModelShape("tp-int8", 256, 768, 2, 4, 2, 96, 32, group_size=64), "llama", "int8", "llama2"),
     "qwen-bias": (ModelShape("tp-qwen", 128, 384, 2, 4, 2, 96, 32, flavour="qwen2"), "qwen", "fp32", "qwen2"),
+    # 8 heads over 2 kv heads: at world 8 four ranks share each kv head (TinyLlama's situation at 8 GPUs)
+    "fp32-gqa8": (ModelShape("tp-gqa8", 256, 512, 2, 8, 2, 96, 32), "llama", "fp32", "llama2"),
+    "int8-gqa8": (ModelShape("tp-int8-gqa8", 512, 2048, 2, 8, 2, 96, 32, group_size=64), "llama", "int8", "llama2"),
 }
 
 
 @pytest.mark.parametrize("key", sorted(LOAD_CASES))
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_load_time_sharding_equals_shard_weights(kllm_lib, tmp_path, key, world):
     shape, family, prec, variant = LOAD_CASES[key]
     try:
